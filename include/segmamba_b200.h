@@ -1,0 +1,177 @@
+/*
+ * segmamba_b200.h -- C ABI of the B200-native SegMamba hot path (libsegmamba_b200.so).
+ *
+ * Plain C: raw device pointers, sizes, element strides, a cudaStream_t passed as void*.  No torch
+ * types.  Every entry point returns 0 on success or a negative SMB_E* code; smb_last_error() then
+ * returns a thread-local message (the Python shim raises it as RuntimeError, which is what the
+ * reference's TORCH_CHECK failures surface as).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repo):
+ *
+ *   smb_scan_fwd      selective_scan_cuda.fwd   mamba/csrc/selective_scan/selective_scan.cpp:226-336
+ *   smb_scan_bwd      selective_scan_cuda.bwd   mamba/csrc/selective_scan/selective_scan.cpp:338-492
+ *   smb_conv1d_fwd    causal_conv1d_cuda.causal_conv1d_fwd   causal-conv1d/csrc/causal_conv1d.cpp:130-189
+ *   smb_conv1d_bwd    causal_conv1d_cuda.causal_conv1d_bwd   causal-conv1d/csrc/causal_conv1d.cpp:191-268
+ *   smb_inner_*       the fused body of MambaInnerFnNoOutProj.forward/backward,
+ *                     mamba/mamba_ssm/ops/selective_scan_interface.py:159-289
+ *   smb_seq_permute   the flip / inter-slice re-orderings of Mamba.forward (v3),
+ *                     mamba/mamba_ssm/modules/mamba_simple.py:230-261
+ *
+ * Scope: real A, input-dependent ("variable") B and C, dstate in {8, 16},
+ * conv width 2..4, non-channel-last conv layout, fp32 / fp16 / bf16 I/O with fp32 arithmetic.
+ * Complex A, constant B/C, channel-last conv and the decode-time `update` kernels are out of scope;
+ * calling with them returns SMB_EUNSUPPORTED.
+ *
+ * Ownership: all buffers are caller-owned and pre-allocated (the reference allocates outputs inside
+ * the binding; here the Python shim does it so the library stays allocator-free).  Accumulated
+ * outputs (dA, dB, dC, dD, ddelta_bias, dweight, dbias) must be zero-initialised by the caller,
+ * exactly like the reference's torch::zeros_like (selective_scan.cpp:460-466, causal_conv1d.cpp:247-249).
+ * Kernels are enqueued asynchronously on `stream`; no host synchronisation happens inside.
+ */
+#ifndef SEGMAMBA_B200_H
+#define SEGMAMBA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SMB_API __attribute__((visibility("default")))
+#else
+#define SMB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMB_OK 0
+#define SMB_EINVAL (-1)        /* bad shape / stride / pointer            */
+#define SMB_EUNSUPPORTED (-2)  /* outside the supported scope (see above) */
+#define SMB_ECUDA (-3)         /* a CUDA runtime call / launch failed     */
+#define SMB_EWORKSPACE (-4)    /* workspace missing or too small          */
+
+/* element type of the activations (u, delta, z, B, C, out, ... ); weights are always fp32 */
+enum { SMB_F32 = 0, SMB_F16 = 1, SMB_BF16 = 2 };
+
+/* order in which the kernel walks the L axis of every (.., L) operand:
+ *   SMB_DIR_FORWARD  token t = position j                 (Mamba.forward `out`,   mamba_simple.py:217)
+ *   SMB_DIR_REVERSE  token t = L-1-j: equals flip(-1) on all inputs and outputs (`out_b`, :230,264) */
+enum { SMB_DIR_FORWARD = 0, SMB_DIR_REVERSE = 1 };
+
+SMB_API int smb_version(void);
+SMB_API const char *smb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Selective scan.
+ *   h[t,n] = exp(dt[t] A[d,n]) h[t-1,n] + dt[t] B[t,n] u[t],   dt = softplus?(delta + delta_bias)
+ *   y[t]   = sum_n C[t,n] h[t,n] + D[d] u[t],   out_z[t] = y[t] * silu(z[t])
+ * Shapes: u, delta, z, out, out_z: (batch, dim, L) with unit L-stride and arbitrary batch / dim
+ * element strides (the reference's "HBL" layout has dim stride = batch*L, selective_scan.cpp:310).
+ * A: (dim, dstate) fp32 contiguous.  D, delta_bias: (dim) fp32 or NULL.
+ * B, C: (batch, n_groups, dstate, L) in the activation dtype; *_ls is the L stride (1 for the
+ * reference layout), *_ns the dstate stride.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct smb_scan_fwd_args {
+    int32_t batch, dim, seqlen, dstate, n_groups;
+    int32_t dtype;           /* SMB_F32 / SMB_F16 / SMB_BF16 */
+    int32_t delta_softplus;  /* bool */
+    int32_t direction;       /* SMB_DIR_* ; 0 reproduces selective_scan_cuda.fwd exactly */
+    const void *u, *delta, *z /* may be NULL */;
+    const float *A, *D /* may be NULL */, *delta_bias /* may be NULL */;
+    const void *B, *C;
+    void *out;       /* y, pre-gate (may be NULL when z != NULL and only out_z is wanted) */
+    void *out_z;     /* required iff z != NULL */
+    float *x;        /* (batch, dim, ceil(L/2048), 2*dstate) chunk states as the reference returns, or NULL */
+    float *hstates;  /* (batch, ceil(L/256)+1, dstate, dim) states at every 256th scan position + final, or NULL;
+                        feed to smb_scan_bwd to skip its forward recompute */
+    int64_t u_bs, u_ds, delta_bs, delta_ds, z_bs, z_ds, out_bs, out_ds, out_z_bs, out_z_ds;
+    int64_t B_bs, B_gs, B_ns, B_ls, C_bs, C_gs, C_ns, C_ls;
+    void *workspace;
+    size_t workspace_bytes;  /* >= smb_scan_fwd_workspace_bytes(...) */
+} smb_scan_fwd_args;
+
+SMB_API size_t smb_scan_fwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
+SMB_API int smb_scan_fwd(const smb_scan_fwd_args *args, void *cuda_stream);
+
+typedef struct smb_scan_bwd_args {
+    int32_t batch, dim, seqlen, dstate, n_groups;
+    int32_t dtype;
+    int32_t delta_softplus;
+    int32_t direction;
+    const void *u, *delta, *z /* may be NULL */;
+    const float *A, *D, *delta_bias;
+    const void *B, *C;
+    const void *dout;           /* gradient of out_z (z != NULL) or of out (z == NULL) */
+    const float *hstates;       /* from smb_scan_fwd, or NULL: recomputed internally */
+    void *du, *ddelta;          /* (batch, dim, L) activation dtype */
+    void *dz;                   /* required iff z != NULL; may alias caller storage (ssi.py:244-248) */
+    void *out_z;                /* optional recomputed out_z (recompute_out_z=True), else NULL */
+    float *dA;                  /* (dim, dstate) fp32, zero-initialised, accumulated */
+    float *dB, *dC;             /* (batch, n_groups, dstate, L) fp32 contiguous, zero-initialised, accumulated */
+    float *dD, *ddelta_bias;    /* (dim) fp32 zero-initialised, or NULL */
+    int64_t u_bs, u_ds, delta_bs, delta_ds, z_bs, z_ds, dout_bs, dout_ds;
+    int64_t du_bs, du_ds, ddelta_bs, ddelta_ds, dz_bs, dz_ds, out_z_bs, out_z_ds;
+    int64_t B_bs, B_gs, B_ns, B_ls, C_bs, C_gs, C_ns, C_ls;
+    void *workspace;
+    size_t workspace_bytes;     /* >= smb_scan_bwd_workspace_bytes(...) */
+} smb_scan_bwd_args;
+
+SMB_API size_t smb_scan_bwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
+SMB_API int smb_scan_bwd(const smb_scan_bwd_args *args, void *cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Depthwise causal conv1d (+ optional SiLU):  out[b,d,t] = act(bias[d] + sum_k w[d,k] x[b,d,t-(W-1-k)])
+ * x, out, dout, dx: (batch, dim, L), unit L-stride.  weight: (dim, width) fp32 with strides,
+ * bias: (dim) fp32 or NULL.  Weights in fp16/bf16 are converted by the shim (the reference's own
+ * call sites always pass fp32 conv weights, ssi.py:169-177).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct smb_conv1d_args {
+    int32_t batch, dim, seqlen, width;
+    int32_t dtype;
+    int32_t silu;
+    int32_t direction;          /* SMB_DIR_REVERSE: causal along descending t (flip folded in) */
+    const void *x;
+    const float *weight, *bias;
+    void *out;
+    int64_t x_bs, x_ds, out_bs, out_ds, w_ds, w_ws;
+} smb_conv1d_args;
+
+SMB_API int smb_conv1d_fwd(const smb_conv1d_args *args, void *cuda_stream);
+
+typedef struct smb_conv1d_bwd_args {
+    int32_t batch, dim, seqlen, width;
+    int32_t dtype;
+    int32_t silu;
+    int32_t direction;
+    const void *x, *dout;
+    const float *weight, *bias;
+    void *dx;                   /* activation dtype; may alias caller storage (ssi.py:281-283) */
+    float *dweight;             /* (dim, width) fp32 contiguous, zero-initialised, accumulated */
+    float *dbias;               /* (dim) fp32 zero-initialised, or NULL */
+    int64_t x_bs, x_ds, dout_bs, dout_ds, dx_bs, dx_ds, w_ds, w_ws;
+} smb_conv1d_bwd_args;
+
+SMB_API int smb_conv1d_bwd(const smb_conv1d_bwd_args *args, void *cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sequence re-ordering used by the inter-slice direction of Mamba.forward (v3):
+ *   to_slices  : dst[.., p*ns + s] = src[.., s*(L/ns) + p]   (stack(chunk(ns)).flatten, mamba_simple.py:245-247)
+ *   from_slices: the inverse                                   (reshape/permute/flatten,   mamba_simple.py:261)
+ * src/dst: (rows, L) with a row stride each, unit L-stride; optionally accumulates (dst += ...).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct smb_seq_permute_args {
+    int32_t rows, seqlen, nslices;
+    int32_t dtype;
+    int32_t inverse;            /* 0: to_slices, 1: from_slices */
+    int32_t accumulate;         /* dst += permuted(src) instead of dst = */
+    const void *src;
+    void *dst;
+    int64_t src_rs, dst_rs;     /* element strides between rows */
+} smb_seq_permute_args;
+
+SMB_API int smb_seq_permute(const smb_seq_permute_args *args, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGMAMBA_B200_H */

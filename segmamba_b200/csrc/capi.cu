@@ -1,0 +1,233 @@
+// extern "C" entry points of libsegmamba_b200.so (see include/segmamba_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/segmamba_b200.h"
+#include "conv_internal.h"
+#include "scan_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *where) {
+    return fail(SMB_ECUDA, "%s: CUDA error %d (%s)", where, (int)e, cudaGetErrorString(e));
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Plan {
+    int dim_per_group, tiles_per_group, n_tiles, S, n_seg, nck;
+    size_t seg_floats, ck_floats;
+};
+
+Plan make_plan(int batch, int dim, int L, int N, int G) {
+    Plan pl;
+    pl.dim_per_group = dim / G;
+    pl.tiles_per_group = (pl.dim_per_group + 31) / 32;
+    pl.n_tiles = pl.tiles_per_group * G;
+    pl.S = smb::plan_segment(batch, pl.n_tiles, L);
+    pl.n_seg = (L + pl.S - 1) / pl.S;
+    pl.nck = (L + smb::kCkpt - 1) / smb::kCkpt;
+    pl.seg_floats = align_up((size_t)batch * pl.n_seg * N * dim, 64);
+    pl.ck_floats = align_up((size_t)batch * (pl.nck + 1) * N * dim, 64);
+    return pl;
+}
+
+int check_common(int batch, int dim, int L, int N, int G, int dtype, const char *who) {
+    if (batch <= 0 || dim <= 0 || L <= 0) return fail(SMB_EINVAL, "%s: batch, dim and seqlen must be positive", who);
+    if (N != 8 && N != 16) return fail(SMB_EUNSUPPORTED, "%s: dstate %d unsupported (8 or 16)", who, N);
+    if (G <= 0 || dim % G != 0) return fail(SMB_EINVAL, "%s: dim %d not divisible by n_groups %d", who, dim, G);
+    if (dtype < SMB_F32 || dtype > SMB_BF16) return fail(SMB_EINVAL, "%s: bad dtype %d", who, dtype);
+    return SMB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+SMB_API int smb_version(void) { return 100; }
+SMB_API const char *smb_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+SMB_API size_t smb_scan_fwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {
+    // worst case over n_groups (more groups -> more tiles -> possibly longer segments -> fewer of them);
+    // G = 1 gives the smallest S, i.e. the largest segment count.
+    const Plan pl = make_plan(batch, dim, seqlen, dstate, 1);
+    Plan plmax = pl;
+    // segment count can only shrink with larger S; be conservative and size for S = kCkpt
+    const int nseg_max = (seqlen + smb::kCkpt - 1) / smb::kCkpt;
+    const size_t seg_floats = align_up((size_t)batch * nseg_max * dstate * dim, 64);
+    return sizeof(float) * (4 * seg_floats + plmax.ck_floats);
+}
+
+SMB_API int smb_scan_fwd(const smb_scan_fwd_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_scan_fwd: null args");
+    int rc = check_common(a->batch, a->dim, a->seqlen, a->dstate, a->n_groups, a->dtype, "smb_scan_fwd");
+    if (rc) return rc;
+    if (!a->u || !a->delta || !a->A || !a->B || !a->C) return fail(SMB_EINVAL, "smb_scan_fwd: u, delta, A, B, C are required");
+    if (a->z && !a->out_z) return fail(SMB_EINVAL, "smb_scan_fwd: out_z is required when z is given");
+    if (!a->z && !a->out) return fail(SMB_EINVAL, "smb_scan_fwd: out is required when z is absent");
+    if (a->B_ls != 1 || a->C_ls != 1) return fail(SMB_EUNSUPPORTED, "smb_scan_fwd: B and C must have unit stride along L");
+    const size_t need = smb_scan_fwd_workspace_bytes(a->batch, a->dim, a->seqlen, a->dstate);
+    if (!a->workspace || a->workspace_bytes < need)
+        return fail(SMB_EWORKSPACE, "smb_scan_fwd: workspace of %zu bytes required, got %zu", need, a->workspace_bytes);
+    const int N = a->dstate;
+    const Plan pl = make_plan(a->batch, a->dim, a->seqlen, N, a->n_groups);
+    smb::ScanP p;
+    memset(&p, 0, sizeof(p));
+    p.batch = a->batch; p.dim = a->dim; p.L = a->seqlen; p.G = a->n_groups;
+    p.dim_per_group = pl.dim_per_group; p.tiles_per_group = pl.tiles_per_group; p.n_tiles = pl.n_tiles;
+    p.S = pl.S; p.n_seg = pl.n_seg; p.nck = pl.nck;
+    p.n_work = a->batch * pl.n_seg * pl.n_tiles;
+    p.reverse = a->direction == SMB_DIR_REVERSE; p.softplus = a->delta_softplus != 0;
+    p.u = a->u; p.delta = a->delta; p.z = a->z; p.B = a->B; p.C = a->C;
+    p.A = a->A; p.D = a->D; p.delta_bias = a->delta_bias;
+    p.out = a->out; p.out_z = a->out_z;
+    p.u_bs = a->u_bs; p.u_ds = a->u_ds; p.delta_bs = a->delta_bs; p.delta_ds = a->delta_ds;
+    p.z_bs = a->z_bs; p.z_ds = a->z_ds; p.out_bs = a->out_bs; p.out_ds = a->out_ds;
+    p.out_z_bs = a->out_z_bs; p.out_z_ds = a->out_z_ds;
+    p.B_bs = a->B_bs; p.B_gs = a->B_gs; p.B_ns = a->B_ns; p.B_ls = a->B_ls;
+    p.C_bs = a->C_bs; p.C_gs = a->C_gs; p.C_ns = a->C_ns; p.C_ls = a->C_ls;
+    float *ws = reinterpret_cast<float *>(a->workspace);
+    const size_t segf = align_up((size_t)a->batch * ((a->seqlen + smb::kCkpt - 1) / smb::kCkpt) * N * a->dim, 64);
+    p.P = ws; p.H = ws + segf; p.hin = ws + 2 * segf; p.cumP = ws + 3 * segf;
+    p.hstates = a->hstates ? a->hstates : (a->x ? ws + 4 * segf : nullptr);
+    cudaError_t e = smb::scan_fwd_dispatch(p, a->dtype, N, a->z != nullptr, a->x, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_scan_fwd");
+    return SMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+SMB_API size_t smb_scan_bwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {
+    const int nck = (seqlen + smb::kCkpt - 1) / smb::kCkpt;
+    const size_t ckf = align_up((size_t)batch * nck * dstate * dim, 64);
+    return sizeof(float) * 6 * ckf;   // Pb, Mloc, Min + (P, H, hin) for the forward-state recompute
+}
+
+SMB_API int smb_scan_bwd(const smb_scan_bwd_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_scan_bwd: null args");
+    int rc = check_common(a->batch, a->dim, a->seqlen, a->dstate, a->n_groups, a->dtype, "smb_scan_bwd");
+    if (rc) return rc;
+    if (!a->u || !a->delta || !a->A || !a->B || !a->C || !a->dout) return fail(SMB_EINVAL, "smb_scan_bwd: u, delta, A, B, C, dout are required");
+    if (!a->du || !a->ddelta || !a->dA || !a->dB || !a->dC) return fail(SMB_EINVAL, "smb_scan_bwd: du, ddelta, dA, dB, dC are required");
+    if (a->z && !a->dz) return fail(SMB_EINVAL, "smb_scan_bwd: dz is required when z is given");
+    if (a->B_ls != 1 || a->C_ls != 1) return fail(SMB_EUNSUPPORTED, "smb_scan_bwd: B and C must have unit stride along L");
+    const size_t need = smb_scan_bwd_workspace_bytes(a->batch, a->dim, a->seqlen, a->dstate);
+    if (!a->workspace || a->workspace_bytes < need)
+        return fail(SMB_EWORKSPACE, "smb_scan_bwd: workspace of %zu bytes required, got %zu", need, a->workspace_bytes);
+    const int N = a->dstate;
+    Plan pl = make_plan(a->batch, a->dim, a->seqlen, N, a->n_groups);
+    smb::ScanP p;
+    memset(&p, 0, sizeof(p));
+    p.batch = a->batch; p.dim = a->dim; p.L = a->seqlen; p.G = a->n_groups;
+    p.dim_per_group = pl.dim_per_group; p.tiles_per_group = pl.tiles_per_group; p.n_tiles = pl.n_tiles;
+    // the backward works on kCkpt-position chunks throughout
+    p.S = smb::kCkpt; p.n_seg = pl.nck; p.nck = pl.nck;
+    p.n_work = a->batch * pl.nck * pl.n_tiles;
+    p.reverse = a->direction == SMB_DIR_REVERSE; p.softplus = a->delta_softplus != 0;
+    p.u = a->u; p.delta = a->delta; p.z = a->z; p.B = a->B; p.C = a->C; p.dout = a->dout;
+    p.A = a->A; p.D = a->D; p.delta_bias = a->delta_bias;
+    p.out_z = a->out_z;
+    p.u_bs = a->u_bs; p.u_ds = a->u_ds; p.delta_bs = a->delta_bs; p.delta_ds = a->delta_ds;
+    p.z_bs = a->z_bs; p.z_ds = a->z_ds; p.dout_bs = a->dout_bs; p.dout_ds = a->dout_ds;
+    p.out_z_bs = a->out_z_bs; p.out_z_ds = a->out_z_ds;
+    p.B_bs = a->B_bs; p.B_gs = a->B_gs; p.B_ns = a->B_ns; p.B_ls = a->B_ls;
+    p.C_bs = a->C_bs; p.C_gs = a->C_gs; p.C_ns = a->C_ns; p.C_ls = a->C_ls;
+    p.du = a->du; p.ddelta = a->ddelta; p.dz = a->dz;
+    p.dA = a->dA; p.dB = a->dB; p.dC = a->dC; p.dD = a->dD; p.ddelta_bias = a->ddelta_bias;
+    p.du_bs = a->du_bs; p.du_ds = a->du_ds; p.ddelta_bs = a->ddelta_bs; p.ddelta_ds = a->ddelta_ds;
+    p.dz_bs = a->dz_bs; p.dz_ds = a->dz_ds;
+    float *ws = reinterpret_cast<float *>(a->workspace);
+    const size_t ckf = align_up((size_t)a->batch * pl.nck * N * a->dim, 64);
+    p.Pb = ws; p.Mloc = ws + ckf; p.Min = ws + 2 * ckf;
+    p.P = ws + 3 * ckf; p.H = ws + 4 * ckf; p.hin = ws + 5 * ckf;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaError_t e;
+    if (a->hstates) {
+        p.hs = a->hstates;
+        p.hs_bs = (int64_t)(pl.nck + 1) * N * a->dim;
+    } else {
+        // recompute the forward states at every chunk start: pass 1 + carry at chunk granularity
+        if (pl.nck > 1) {
+            if ((e = smb::scan_fwd_agg_dispatch(p, a->dtype, N, st)) != cudaSuccess) return cuda_fail(e, "smb_scan_bwd(agg)");
+            if ((e = smb::carry_launch(p.P, p.H, p.hin, nullptr, a->batch, pl.nck, N, a->dim, 0, st)) != cudaSuccess)
+                return cuda_fail(e, "smb_scan_bwd(carry)");
+        } else {
+            if ((e = cudaMemsetAsync(p.hin, 0, sizeof(float) * (size_t)a->batch * N * a->dim, st)) != cudaSuccess)
+                return cuda_fail(e, "smb_scan_bwd(memset)");
+        }
+        p.hs = p.hin;
+        p.hs_bs = (int64_t)pl.nck * N * a->dim;
+    }
+    e = smb::scan_bwd_dispatch(p, a->dtype, N, a->z != nullptr, st);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_scan_bwd");
+    return SMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int conv_common(int batch, int dim, int L, int width, int dtype, const char *who) {
+    if (batch <= 0 || dim <= 0 || L <= 0) return fail(SMB_EINVAL, "%s: batch, dim and seqlen must be positive", who);
+    if (width < 2 || width > 4) return fail(SMB_EUNSUPPORTED, "%s: only widths 2..4 are supported (got %d)", who, width);
+    if (dtype < SMB_F32 || dtype > SMB_BF16) return fail(SMB_EINVAL, "%s: bad dtype %d", who, dtype);
+    if (dim > 65535 || batch > 65535) return fail(SMB_EINVAL, "%s: dim and batch are limited to 65535", who);
+    return SMB_OK;
+}
+
+SMB_API int smb_conv1d_fwd(const smb_conv1d_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_conv1d_fwd: null args");
+    int rc = conv_common(a->batch, a->dim, a->seqlen, a->width, a->dtype, "smb_conv1d_fwd");
+    if (rc) return rc;
+    if (!a->x || !a->weight || !a->out) return fail(SMB_EINVAL, "smb_conv1d_fwd: x, weight, out are required");
+    smb::ConvP p;
+    memset(&p, 0, sizeof(p));
+    p.batch = a->batch; p.dim = a->dim; p.L = a->seqlen; p.width = a->width;
+    p.silu = a->silu != 0; p.reverse = a->direction == SMB_DIR_REVERSE;
+    p.x = a->x; p.weight = a->weight; p.bias = a->bias; p.out = a->out;
+    p.x_bs = a->x_bs; p.x_ds = a->x_ds; p.out_bs = a->out_bs; p.out_ds = a->out_ds; p.w_ds = a->w_ds; p.w_ws = a->w_ws;
+    cudaError_t e = smb::conv1d_dispatch(p, a->dtype, false, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_conv1d_fwd");
+    return SMB_OK;
+}
+
+SMB_API int smb_conv1d_bwd(const smb_conv1d_bwd_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_conv1d_bwd: null args");
+    int rc = conv_common(a->batch, a->dim, a->seqlen, a->width, a->dtype, "smb_conv1d_bwd");
+    if (rc) return rc;
+    if (!a->x || !a->weight || !a->dout || !a->dx || !a->dweight) return fail(SMB_EINVAL, "smb_conv1d_bwd: x, weight, dout, dx, dweight are required");
+    smb::ConvP p;
+    memset(&p, 0, sizeof(p));
+    p.batch = a->batch; p.dim = a->dim; p.L = a->seqlen; p.width = a->width;
+    p.silu = a->silu != 0; p.reverse = a->direction == SMB_DIR_REVERSE;
+    p.x = a->x; p.dout = a->dout; p.weight = a->weight; p.bias = a->bias; p.dx = a->dx;
+    p.dweight = a->dweight; p.dbias = a->dbias;
+    p.x_bs = a->x_bs; p.x_ds = a->x_ds; p.dout_bs = a->dout_bs; p.dout_ds = a->dout_ds; p.dx_bs = a->dx_bs; p.dx_ds = a->dx_ds;
+    p.w_ds = a->w_ds; p.w_ws = a->w_ws;
+    cudaError_t e = smb::conv1d_dispatch(p, a->dtype, true, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_conv1d_bwd");
+    return SMB_OK;
+}
+
+SMB_API int smb_seq_permute(const smb_seq_permute_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_seq_permute: null args");
+    if (a->rows <= 0 || a->seqlen <= 0 || a->nslices <= 0) return fail(SMB_EINVAL, "smb_seq_permute: rows, seqlen, nslices must be positive");
+    if (a->seqlen % a->nslices != 0) return fail(SMB_EINVAL, "smb_seq_permute: seqlen %d not divisible by nslices %d", a->seqlen, a->nslices);
+    if (a->rows > 65535) return fail(SMB_EINVAL, "smb_seq_permute: rows limited to 65535");
+    if (a->dtype < SMB_F32 || a->dtype > SMB_BF16) return fail(SMB_EINVAL, "smb_seq_permute: bad dtype");
+    if (!a->src || !a->dst) return fail(SMB_EINVAL, "smb_seq_permute: src and dst are required");
+    cudaError_t e = smb::seq_permute_dispatch(a->src, a->dst, a->src_rs, a->dst_rs, a->rows, a->seqlen, a->nslices, a->inverse,
+                                              a->accumulate, a->dtype, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_seq_permute");
+    return SMB_OK;
+}
+
+}  // extern "C"

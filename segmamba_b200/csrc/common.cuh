@@ -1,0 +1,270 @@
+// Shared device helpers for the sm_100a scan / conv kernels.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace smb {
+
+constexpr int kTile = 32;         // scan positions per warp-private shared-memory tile
+constexpr int kCkpt = 256;        // state checkpoint interval (scan positions) shared by fwd and bwd
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// ---------------------------------------------------------------------------------------------
+// math.  The decay uses the MUFU ex2 path with A pre-scaled by log2(e), as the reference kernel
+// does (selective_scan_fwd_kernel.cuh:169-171,216).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softplus with the reference's threshold (selective_scan_fwd_kernel.cuh:155)
+__device__ __forceinline__ float softplus20(float x) { return x <= 20.f ? log1pf(__expf(x)) : x; }
+__device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------
+// element conversion
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 4 consecutive elements <-> float4; the pointer must be aligned to 4 elements.
+template <typename T> __device__ __forceinline__ float4 load4(const T *p);
+template <> __device__ __forceinline__ float4 load4<float>(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+template <> __device__ __forceinline__ float4 load4<__half>(const __half *p) {
+    uint2 r = *reinterpret_cast<const uint2 *>(p);
+    __half2 a = *reinterpret_cast<__half2 *>(&r.x), b = *reinterpret_cast<__half2 *>(&r.y);
+    float2 fa = __half22float2(a), fb = __half22float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    uint2 r = *reinterpret_cast<const uint2 *>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162 *>(&r.x), b = *reinterpret_cast<__nv_bfloat162 *>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T *p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+template <> __device__ __forceinline__ void store4<__half>(__half *p, float4 v) {
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t *>(&a);
+    r.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = r;
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16 *p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t *>(&a);
+    r.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = r;
+}
+template <typename T> __device__ __forceinline__ bool aligned4(const T *p) {
+    return (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(T) - 1)) == 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-private activation tile: 32 rows (channels) x 32 scan positions, fp32, 128-byte rows with
+// an XOR swizzle on the 16-byte chunk index so that both access patterns are conflict-free:
+//   fill/store: 8 lanes cover one row's 8 chunks (coalesced 128 B global segments);
+//   compute   : lane == row reads chunk c (4 consecutive positions) with one LDS.128.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tile_chunk_off(int row, int c) { return row * kTile + (((c ^ (row & 7))) << 2); }
+__device__ __forceinline__ float4 tile_read4(const float *tile, int row, int c) {
+    return *reinterpret_cast<const float4 *>(tile + tile_chunk_off(row, c));
+}
+__device__ __forceinline__ void tile_write4(float *tile, int row, int c, float4 v) {
+    *reinterpret_cast<float4 *>(tile + tile_chunk_off(row, c)) = v;
+}
+
+// Scan position j <-> token index t along L.
+__device__ __forceinline__ int pos_to_tok(int j, int L, bool reverse) { return reverse ? L - 1 - j : j; }
+
+// Fill a tile with scan positions [j0, j0+32) of `nrows` rows; rows >= nrows and positions >= L read 0.
+// base points at (row 0, token 0); row_stride in elements.
+template <typename T>
+__device__ __forceinline__ void fill_tile(float *tile, const T *base, int64_t row_stride, int nrows, int j0, int L,
+                                          bool reverse, int lane) {
+    float4 v[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int unit = it * 32 + lane;
+        const int row = unit >> 3, c = unit & 7;
+        const int jl = j0 + 4 * c;               // first scan position of the chunk
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < nrows && jl < L) {
+            const T *rp = base + (int64_t)row * row_stride;
+            if (!reverse) {
+                const T *p = rp + jl;
+                if (jl + 3 < L && aligned4(p)) {
+                    r = load4<T>(p);
+                } else {
+                    r.x = to_f32<T>(p[0]);
+                    if (jl + 1 < L) r.y = to_f32<T>(p[1]);
+                    if (jl + 2 < L) r.z = to_f32<T>(p[2]);
+                    if (jl + 3 < L) r.w = to_f32<T>(p[3]);
+                }
+            } else {
+                const int th = L - 1 - jl;       // token of position jl (highest of the chunk)
+                const T *p = rp + (th - 3);
+                if (th - 3 >= 0 && aligned4(p)) {
+                    float4 q = load4<T>(p);
+                    r = make_float4(q.w, q.z, q.y, q.x);
+                } else {
+                    r.x = to_f32<T>(rp[th]);
+                    if (th - 1 >= 0) r.y = to_f32<T>(rp[th - 1]);
+                    if (th - 2 >= 0) r.z = to_f32<T>(rp[th - 2]);
+                    if (th - 3 >= 0) r.w = to_f32<T>(rp[th - 3]);
+                }
+            }
+        }
+        v[it] = r;
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int unit = it * 32 + lane;
+        tile_write4(tile, unit >> 3, unit & 7, v[it]);
+    }
+}
+
+// Inverse of fill_tile: write scan positions [j0, j0+32) of `nrows` rows back to global memory.
+template <typename T>
+__device__ __forceinline__ void store_tile(const float *tile, T *base, int64_t row_stride, int nrows, int j0, int L,
+                                           bool reverse, int lane) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int unit = it * 32 + lane;
+        const int row = unit >> 3, c = unit & 7;
+        const int jl = j0 + 4 * c;
+        if (row < nrows && jl < L) {
+            const float4 r = tile_read4(tile, row, c);
+            T *rp = base + (int64_t)row * row_stride;
+            if (!reverse) {
+                T *p = rp + jl;
+                if (jl + 3 < L && aligned4(p)) {
+                    store4<T>(p, r);
+                } else {
+                    p[0] = from_f32<T>(r.x);
+                    if (jl + 1 < L) p[1] = from_f32<T>(r.y);
+                    if (jl + 2 < L) p[2] = from_f32<T>(r.z);
+                    if (jl + 3 < L) p[3] = from_f32<T>(r.w);
+                }
+            } else {
+                const int th = L - 1 - jl;
+                T *p = rp + (th - 3);
+                if (th - 3 >= 0 && aligned4(p)) {
+                    store4<T>(p, make_float4(r.w, r.z, r.y, r.x));
+                } else {
+                    rp[th] = from_f32<T>(r.x);
+                    if (th - 1 >= 0) rp[th - 1] = from_f32<T>(r.y);
+                    if (th - 2 >= 0) rp[th - 2] = from_f32<T>(r.z);
+                    if (th - 3 >= 0) rp[th - 3] = from_f32<T>(r.w);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-private B / C tile: 32 scan positions x N states, position-major so that one position's
+// states are read with broadcast LDS.128 by every lane (lane == channel).  The 16-byte chunk
+// index is XOR-swizzled with (q>>1) to spread the transposing fill over 8 bank groups.
+// ---------------------------------------------------------------------------------------------
+template <int N> __device__ __forceinline__ int bc_off(int q, int n) {
+    return q * N + ((((n >> 2) ^ ((q >> 1) & (N / 4 - 1)))) << 2) + (n & 3);
+}
+template <int N> __device__ __forceinline__ float4 bc_read4(const float *tile, int q, int chunk) {
+    return *reinterpret_cast<const float4 *>(tile + q * N + (((chunk ^ ((q >> 1) & (N / 4 - 1)))) << 2));
+}
+// base points at (state 0, token 0) of the (dstate, L) slab; ns / ls are the state / token strides.
+template <typename T, int N>
+__device__ __forceinline__ void fill_bc_tile(float *tile, const T *base, int64_t ns, int64_t ls, int j0, int L,
+                                             bool reverse, int lane) {
+    const int j = j0 + lane;
+    const bool valid = j < L;
+    const int64_t toff = (int64_t)pos_to_tok(valid ? j : 0, L, reverse) * ls;
+    float v[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) v[n] = valid ? to_f32<T>(base[(int64_t)n * ns + toff]) : 0.f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) tile[bc_off<N>(lane, n)] = v[n];
+}
+
+constexpr int kRun = 8;           // positions per lane in the run-per-lane kernels (bwd scan, conv1d)
+
+// ---------------------------------------------------------------------------------------------
+// per-lane runs of 8 consecutive scan positions straight from / to global memory
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void load_run8(const T *row, int j, int L, bool reverse, float v[kRun]) {
+#pragma unroll
+    for (int i = 0; i < kRun; ++i) v[i] = 0.f;
+    if (j >= L) return;
+    if (!reverse) {
+        const T *p = row + j;
+        if (j + 7 < L && aligned4(p)) {
+            const float4 a = load4<T>(p), b = load4<T>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) if (j + i < L) v[i] = to_f32<T>(p[i]);
+        }
+    } else {
+        const int th = L - 1 - j;
+        const T *p = row + (th - 7);
+        if (th - 7 >= 0 && aligned4(p)) {
+            const float4 a = load4<T>(p), b = load4<T>(p + 4);
+            v[7] = a.x; v[6] = a.y; v[5] = a.z; v[4] = a.w; v[3] = b.x; v[2] = b.y; v[1] = b.z; v[0] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) if (th - i >= 0) v[i] = to_f32<T>(row[th - i]);
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_run8(T *row, int j, int L, bool reverse, const float v[kRun]) {
+    if (j >= L) return;
+    if (!reverse) {
+        T *p = row + j;
+        if (j + 7 < L && aligned4(p)) {
+            store4<T>(p, make_float4(v[0], v[1], v[2], v[3]));
+            store4<T>(p + 4, make_float4(v[4], v[5], v[6], v[7]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) if (j + i < L) p[i] = from_f32<T>(v[i]);
+        }
+    } else {
+        const int th = L - 1 - j;
+        T *p = row + (th - 7);
+        if (th - 7 >= 0 && aligned4(p)) {
+            store4<T>(p, make_float4(v[7], v[6], v[5], v[4]));
+            store4<T>(p + 4, make_float4(v[3], v[2], v[1], v[0]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) if (th - i >= 0) row[th - i] = from_f32<T>(v[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace smb

@@ -1,0 +1,374 @@
+// Backward selective scan for sm_100a: chunk-parallel, three passes over 256-position chunks.
+//
+//   R1  scan_bwd_ragg_kernel  lane-per-channel reverse walk of each chunk with zero incoming adjoint:
+//                             (P = prod a, Mloc = adjoint at the chunk start)                     [1 ex2 / update]
+//   R2  carry_kernel          reverse exclusive scan of (P, Mloc) over chunks -> Min per chunk    [tiny]
+//   R3  scan_bwd_main_kernel  warp-per-channel, 8 positions per lane in registers: forward state recompute
+//                             seeded from the saved chunk state, reverse adjoint scan seeded from Min, all
+//                             gradients; dB/dC are reduced over the CTA's channels in shared memory before
+//                             ONE fp32 atomic per (state, position) per CTA (the reference issues one per
+//                             channel, selective_scan_bwd_kernel.cuh:297-316)                      [1 ex2 / update]
+//
+// Adjoint recurrence in "mu" form (mu_t = a_t lambda_t, the gradient w.r.t. h_{t-1}), which needs no
+// a_{t+1} look-ahead across lanes/chunks (the reference fetches it through smem_delta_a, :244-262):
+//     lambda_t = g_t C_t + mu_{t+1},      mu_t = a_t lambda_t
+// Gradients (SURVEY.md Appendix D / selective_scan_bwd_kernel.cuh:276-294,439-453):
+//     du  = dt * sum_n lambda B + D g            ddt = u * sum_n lambda B + sum_n lambda A (h - b)
+//     dA  = sum_t lambda dt (h - b)              dB  = sum_d lambda dt u        dC = sum_d g h
+//     ddelta = ddt * sigmoid(delta + bias) (softplus)     dz = dout y sigmoid(z)(1 + z(1 - sigmoid(z)))
+#include "scan_internal.h"
+
+namespace smb {
+
+constexpr int kBwdWarps = 8;               // channels per CTA in R3
+constexpr int kRowPad = kCkpt + 32;        // padded smem row: position p lives at p + (p>>5)*4
+static_assert(kRun * 32 == kCkpt, "R3 chunk must equal the checkpoint interval");
+
+__device__ __forceinline__ int pad_pos(int p) { return p + ((p >> 5) << 2); }
+
+// ---------------------------------------------------------------------------------------------
+// R1: reverse aggregate per chunk (lane == channel)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int N, bool kHasZ>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const ScanP p) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kWarpsPerCta + warp;
+    if (w >= p.n_work) return;
+    const WorkItem wi = decode_work(p, w);          // here S == kCkpt, n_seg == nck
+    const int d = wi.d0 + lane;
+    const bool active = lane < wi.nrows;
+
+    float *s_dt = smem + warp * (3 * kTile * kTile + kTile * N);
+    float *s_g = s_dt + kTile * kTile;
+    float *s_z = s_g + kTile * kTile;
+    float *s_C = s_z + kTile * kTile;
+
+    float A2[N], mu[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        A2[n] = active ? p.A[(int64_t)d * N + n] * kLog2e : 0.f;
+        mu[n] = 0.f;
+    }
+    const float bias = (active && p.delta_bias) ? p.delta_bias[d] : 0.f;
+    float sumdt = 0.f;
+
+    const T *dl = reinterpret_cast<const T *>(p.delta) + wi.b * p.delta_bs + (int64_t)wi.d0 * p.delta_ds;
+    const T *go = reinterpret_cast<const T *>(p.dout) + wi.b * p.dout_bs + (int64_t)wi.d0 * p.dout_ds;
+    const T *z = kHasZ ? reinterpret_cast<const T *>(p.z) + wi.b * p.z_bs + (int64_t)wi.d0 * p.z_ds : nullptr;
+    const T *Cm = reinterpret_cast<const T *>(p.C) + wi.b * p.C_bs + (int64_t)wi.g * p.C_gs;
+
+    const int j_begin = wi.seg * kCkpt;
+    const int j_end = min(p.L, j_begin + kCkpt);
+    const int last_tile = j_begin + ((j_end - j_begin - 1) / kTile) * kTile;
+    for (int j0 = last_tile; j0 >= j_begin; j0 -= kTile) {
+        fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
+        fill_tile<T>(s_g, go, p.dout_ds, wi.nrows, j0, p.L, p.reverse, lane);
+        if (kHasZ) fill_tile<T>(s_z, z, p.z_ds, wi.nrows, j0, p.L, p.reverse, lane);
+        fill_bc_tile<T, N>(s_C, Cm, p.C_ns, p.C_ls, j0, p.L, p.reverse, lane);
+        __syncwarp();
+        const int qmax = min(kTile, j_end - j0);
+        for (int c = (qmax - 1) >> 2; c >= 0; --c) {
+            const float4 d4 = tile_read4(s_dt, lane, c);
+            const float4 g4 = tile_read4(s_g, lane, c);
+            float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kHasZ) z4 = tile_read4(s_z, lane, c);
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+            for (int e = 3; e >= 0; --e) {
+                const int q = 4 * c + e;
+                if (q < qmax) {
+                    float dt = dd[e] + bias;
+                    if (p.softplus) dt = softplus20(dt);
+                    float g = gg[e];
+                    if (kHasZ) g *= zz[e] * sigmoidf(zz[e]);
+                    sumdt += dt;
+#pragma unroll
+                    for (int jn = 0; jn < N / 4; ++jn) {
+                        const float4 c4 = bc_read4<N>(s_C, q, jn);
+                        const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int n = 4 * jn + k;
+                            const float a = ex2(dt * A2[n]);
+                            mu[n] = a * fmaf(g, cc[k], mu[n]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (active) {
+        const int64_t o = (((int64_t)wi.b * p.n_seg + wi.seg) * N) * p.dim + d;
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            p.Pb[o + (int64_t)n * p.dim] = ex2(A2[n] * sumdt);
+            p.Mloc[o + (int64_t)n * p.dim] = mu[n];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// R3: main backward kernel (warp == channel, lane == run of 8 positions, CTA == 8 channels)
+// grid = (chunks, channel octets (group-aligned), batch)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int N, bool kHasZ>
+__global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const ScanP p) {
+    extern __shared__ __align__(16) float smem[];
+    float *sB = smem;                                  // [N][kRowPad]
+    float *sC = sB + N * kRowPad;                      // [N][kRowPad]
+    float *slabB = sC + N * kRowPad;                   // [kBwdWarps][kRowPad]
+    float *slabC = slabB + kBwdWarps * kRowPad;        // [kBwdWarps][kRowPad]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.x, b = blockIdx.z;
+    const int octs_per_group = (p.dim_per_group + kBwdWarps - 1) / kBwdWarps;
+    const int g = blockIdx.y / octs_per_group;
+    const int d0 = g * p.dim_per_group + (blockIdx.y - g * octs_per_group) * kBwdWarps;
+    const int nch = min(kBwdWarps, (g + 1) * p.dim_per_group - d0);   // active channels (warps) in this CTA
+    const int d = d0 + warp;
+    const bool active = warp < nch;
+    const int jc = chunk * kCkpt;                      // first scan position of the chunk
+    const int jl = jc + lane * kRun;                   // first scan position of this lane's run
+    const bool rev = p.reverse;
+    const int L = p.L;
+
+    // ---- stage B and C for the chunk: thread t <-> position jc + t ----
+    {
+        const T *Bm = reinterpret_cast<const T *>(p.B) + b * p.B_bs + (int64_t)g * p.B_gs;
+        const T *Cm = reinterpret_cast<const T *>(p.C) + b * p.C_bs + (int64_t)g * p.C_gs;
+        const int t = threadIdx.x;
+        const int j = jc + t;
+        const bool valid = j < L;
+        const int tok = pos_to_tok(valid ? j : 0, L, rev);
+        const int so = pad_pos(t);
+#pragma unroll 4
+        for (int n = 0; n < N; ++n) {
+            sB[n * kRowPad + so] = valid ? to_f32<T>(Bm[(int64_t)n * p.B_ns + (int64_t)tok * p.B_ls]) : 0.f;
+            sC[n * kRowPad + so] = valid ? to_f32<T>(Cm[(int64_t)n * p.C_ns + (int64_t)tok * p.C_ls]) : 0.f;
+        }
+    }
+
+    // ---- per-lane runs ----
+    float dt[kRun], uu[kRun], gg[kRun], sLB[kRun], sAq[kRun], yy[kRun];
+    float bias = 0.f, Dv = 0.f;
+    if (active) {
+        bias = p.delta_bias ? p.delta_bias[d] : 0.f;
+        Dv = p.D ? p.D[d] : 0.f;
+        const T *ur = reinterpret_cast<const T *>(p.u) + b * p.u_bs + (int64_t)d * p.u_ds;
+        const T *dr = reinterpret_cast<const T *>(p.delta) + b * p.delta_bs + (int64_t)d * p.delta_ds;
+        const T *gr = reinterpret_cast<const T *>(p.dout) + b * p.dout_bs + (int64_t)d * p.dout_ds;
+        load_run8<T>(ur, jl, L, rev, uu);
+        load_run8<T>(dr, jl, L, rev, dt);
+        load_run8<T>(gr, jl, L, rev, gg);
+        if (kHasZ) {
+            float zz[kRun];
+            const T *zr = reinterpret_cast<const T *>(p.z) + b * p.z_bs + (int64_t)d * p.z_ds;
+            load_run8<T>(zr, jl, L, rev, zz);
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) gg[i] *= zz[i] * sigmoidf(zz[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < kRun; ++i) {
+            float v = dt[i] + bias;
+            if (p.softplus) v = softplus20(v);
+            dt[i] = (jl + i < L) ? v : 0.f;             // masked positions are scan identities (a=1, b=0)
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kRun; ++i) { dt[i] = 0.f; uu[i] = 0.f; gg[i] = 0.f; }
+    }
+#pragma unroll
+    for (int i = 0; i < kRun; ++i) { sLB[i] = 0.f; sAq[i] = 0.f; yy[i] = 0.f; }
+
+    __syncthreads();   // B/C tiles ready
+
+    const int64_t hs_off = (int64_t)b * p.hs_bs + ((int64_t)chunk * N) * p.dim + d;
+    const int64_t mi_off = (((int64_t)b * p.nck + chunk) * N) * p.dim + d;
+    const int bo = pad_pos(lane * kRun);               // this lane's run inside a padded row
+    float *myB = slabB + warp * kRowPad + bo;
+    float *myC = slabC + warp * kRowPad + bo;
+
+#pragma unroll 1
+    for (int n = 0; n < N; ++n) {
+        float dBv[kRun], dCv[kRun];
+        if (active) {
+            const float A2n = p.A[(int64_t)d * N + n] * kLog2e;
+            const float h_in = p.hs[hs_off + (int64_t)n * p.dim];
+            const float m_in = p.Min[mi_off + (int64_t)n * p.dim];
+            float Bv[kRun], Cv[kRun];
+            {
+                const float4 b0 = *reinterpret_cast<const float4 *>(sB + n * kRowPad + bo);
+                const float4 b1 = *reinterpret_cast<const float4 *>(sB + n * kRowPad + bo + 4);
+                const float4 c0 = *reinterpret_cast<const float4 *>(sC + n * kRowPad + bo);
+                const float4 c1 = *reinterpret_cast<const float4 *>(sC + n * kRowPad + bo + 4);
+                Bv[0] = b0.x; Bv[1] = b0.y; Bv[2] = b0.z; Bv[3] = b0.w; Bv[4] = b1.x; Bv[5] = b1.y; Bv[6] = b1.z; Bv[7] = b1.w;
+                Cv[0] = c0.x; Cv[1] = c0.y; Cv[2] = c0.z; Cv[3] = c0.w; Cv[4] = c1.x; Cv[5] = c1.y; Cv[6] = c1.z; Cv[7] = c1.w;
+            }
+            float a[kRun], bb[kRun], hs[kRun];
+            // lane aggregates of the forward recurrence
+            float Aagg = 1.f, Hagg = 0.f;
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) {
+                a[i] = ex2(dt[i] * A2n);
+                bb[i] = dt[i] * uu[i] * Bv[i];
+                Hagg = fmaf(a[i], Hagg, bb[i]);
+                Aagg *= a[i];
+            }
+            // exclusive forward warp scan -> state entering this lane's run
+            float As = Aagg, Hs = Hagg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float Au = __shfl_up_sync(0xffffffffu, As, o), Hu = __shfl_up_sync(0xffffffffu, Hs, o);
+                if (lane >= o) { Hs = fmaf(As, Hu, Hs); As *= Au; }
+            }
+            float Ae = __shfl_up_sync(0xffffffffu, As, 1), He = __shfl_up_sync(0xffffffffu, Hs, 1);
+            if (lane == 0) { Ae = 1.f; He = 0.f; }
+            float h = fmaf(Ae, h_in, He);
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) { h = fmaf(a[i], h, bb[i]); hs[i] = h; }
+            // lane aggregates of the reverse (adjoint) recurrence  mu_i = a_i (mu_{i+1} + g_i C_i)
+            float Magg = 0.f;
+#pragma unroll
+            for (int i = kRun - 1; i >= 0; --i) Magg = a[i] * fmaf(gg[i], Cv[i], Magg);
+            float Ar = Aagg, Mr = Magg;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float Ad = __shfl_down_sync(0xffffffffu, Ar, o), Md = __shfl_down_sync(0xffffffffu, Mr, o);
+                if (lane + o < 32) { Mr = fmaf(Ar, Md, Mr); Ar *= Ad; }
+            }
+            float Ax = __shfl_down_sync(0xffffffffu, Ar, 1), Mx = __shfl_down_sync(0xffffffffu, Mr, 1);
+            if (lane == 31) { Ax = 1.f; Mx = 0.f; }
+            float m = fmaf(Ax, m_in, Mx);                // mu entering this run from the right
+            float dAacc = 0.f;
+#pragma unroll
+            for (int i = kRun - 1; i >= 0; --i) {
+                const float lam = fmaf(gg[i], Cv[i], m);
+                m = a[i] * lam;
+                yy[i] = fmaf(Cv[i], hs[i], yy[i]);
+                dCv[i] = gg[i] * hs[i];
+                dBv[i] = lam * dt[i] * uu[i];
+                sLB[i] = fmaf(lam, Bv[i], sLB[i]);
+                const float qv = lam * (hs[i] - bb[i]);
+                dAacc = fmaf(dt[i], qv, dAacc);
+                sAq[i] = fmaf(A2n, qv, sAq[i]);
+            }
+            dAacc = warp_sum(dAacc);                    // dA_n = sum_t lambda dt (h - b)
+            if (lane == 0) atomicAdd(p.dA + (int64_t)d * N + n, dAacc);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kRun; ++i) { dBv[i] = 0.f; dCv[i] = 0.f; }
+        }
+        // ---- reduce dB / dC over the CTA's channels ----
+        *reinterpret_cast<float4 *>(myB) = make_float4(dBv[0], dBv[1], dBv[2], dBv[3]);
+        *reinterpret_cast<float4 *>(myB + 4) = make_float4(dBv[4], dBv[5], dBv[6], dBv[7]);
+        *reinterpret_cast<float4 *>(myC) = make_float4(dCv[0], dCv[1], dCv[2], dCv[3]);
+        *reinterpret_cast<float4 *>(myC + 4) = make_float4(dCv[4], dCv[5], dCv[6], dCv[7]);
+        __syncthreads();
+        {
+            const int t = threadIdx.x;
+            const int j = jc + t;
+            if (j < L) {
+                const int so = pad_pos(t);
+                float sb = 0.f, sc = 0.f;
+                for (int w2 = 0; w2 < nch; ++w2) {
+                    sb += slabB[w2 * kRowPad + so];
+                    sc += slabC[w2 * kRowPad + so];
+                }
+                const int tok = pos_to_tok(j, L, rev);
+                const int64_t o = (((int64_t)b * p.G + g) * N + n) * (int64_t)L + tok;
+                atomicAdd(p.dB + o, sb);
+                atomicAdd(p.dC + o, sc);
+            }
+        }
+        __syncthreads();
+    }
+
+    if (!active) return;
+    // ---- epilogue: du, ddelta, dz, (out_z), dD, ddelta_bias ----
+    float duv[kRun], ddv[kRun];
+    float dDacc = 0.f, dbacc = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRun; ++i) {
+        duv[i] = fmaf(dt[i], sLB[i], Dv * gg[i]);
+        float ddt = fmaf(uu[i], sLB[i], kLn2 * sAq[i]);
+        if (p.softplus) ddt *= -expm1f(-dt[i]);          // sigmoid(raw) == 1 - exp(-softplus(raw))
+        if (jl + i >= L) ddt = 0.f;
+        ddv[i] = ddt;
+        dDacc = fmaf(gg[i], uu[i], dDacc);
+        dbacc += ddt;
+    }
+    {
+        T *dur = reinterpret_cast<T *>(p.du) + b * p.du_bs + (int64_t)d * p.du_ds;
+        T *ddr = reinterpret_cast<T *>(p.ddelta) + b * p.ddelta_bs + (int64_t)d * p.ddelta_ds;
+        store_run8<T>(dur, jl, L, rev, duv);
+        store_run8<T>(ddr, jl, L, rev, ddv);
+    }
+    if (kHasZ) {
+        float zz[kRun], go[kRun], dzv[kRun], ozv[kRun];
+        const T *zr = reinterpret_cast<const T *>(p.z) + b * p.z_bs + (int64_t)d * p.z_ds;
+        const T *gr = reinterpret_cast<const T *>(p.dout) + b * p.dout_bs + (int64_t)d * p.dout_ds;
+        load_run8<T>(zr, jl, L, rev, zz);
+        load_run8<T>(gr, jl, L, rev, go);
+#pragma unroll
+        for (int i = 0; i < kRun; ++i) {
+            const float y = fmaf(Dv, uu[i], yy[i]);
+            const float sg = sigmoidf(zz[i]);
+            dzv[i] = go[i] * y * sg * (1.f + zz[i] * (1.f - sg));
+            ozv[i] = y * zz[i] * sg;
+        }
+        T *dzr = reinterpret_cast<T *>(p.dz) + b * p.dz_bs + (int64_t)d * p.dz_ds;
+        store_run8<T>(dzr, jl, L, rev, dzv);
+        if (p.out_z) {
+            T *ozr = reinterpret_cast<T *>(p.out_z) + b * p.out_z_bs + (int64_t)d * p.out_z_ds;
+            store_run8<T>(ozr, jl, L, rev, ozv);
+        }
+    }
+    dDacc = warp_sum(dDacc);
+    dbacc = warp_sum(dbacc);
+    if (lane == 0) {
+        if (p.dD) atomicAdd(p.dD + d, dDacc);
+        if (p.ddelta_bias) atomicAdd(p.ddelta_bias + d, dbacc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <typename T, int N, bool kHasZ>
+static cudaError_t launch_bwd(const ScanP &p, cudaStream_t st) {
+    cudaError_t e;
+    // R1
+    const int ctas = (p.n_work + kWarpsPerCta - 1) / kWarpsPerCta;
+    const size_t sm1 = (size_t)kWarpsPerCta * (3 * kTile * kTile + kTile * N) * sizeof(float);
+    if ((e = cudaFuncSetAttribute(scan_bwd_ragg_kernel<T, N, kHasZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
+    scan_bwd_ragg_kernel<T, N, kHasZ><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p);
+    // R2
+    if ((e = carry_launch(p.Pb, p.Mloc, p.Min, nullptr, p.batch, p.nck, N, p.dim, 1, st)) != cudaSuccess) return e;
+    // R3
+    const size_t sm3 = (size_t)(2 * N + 2 * kBwdWarps) * kRowPad * sizeof(float);
+    if ((e = cudaFuncSetAttribute(scan_bwd_main_kernel<T, N, kHasZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
+    const int octs = ((p.dim_per_group + kBwdWarps - 1) / kBwdWarps) * p.G;
+    dim3 grid(p.nck, octs, p.batch);
+    scan_bwd_main_kernel<T, N, kHasZ><<<grid, kBwdWarps * 32, sm3, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_bwd_t(const ScanP &p, int N, bool has_z, cudaStream_t st) {
+    if (N == 16) return has_z ? launch_bwd<T, 16, true>(p, st) : launch_bwd<T, 16, false>(p, st);
+    return has_z ? launch_bwd<T, 8, true>(p, st) : launch_bwd<T, 8, false>(p, st);
+}
+
+cudaError_t scan_bwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, cudaStream_t st) {
+    switch (dtype) {
+        case 0: return launch_bwd_t<float>(p, N, has_z, st);
+        case 1: return launch_bwd_t<__half>(p, N, has_z, st);
+        default: return launch_bwd_t<__nv_bfloat16>(p, N, has_z, st);
+    }
+}
+
+}  // namespace smb

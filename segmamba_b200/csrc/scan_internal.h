@@ -1,0 +1,65 @@
+// Internal parameter block shared by the scan kernels (device + host).
+#pragma once
+
+#include "common.cuh"
+
+namespace smb {
+
+constexpr int kWarpsPerCta = 4;   // independent warps per CTA in the lane-per-channel kernels
+
+struct ScanP {
+    int batch, dim, L, G;
+    int dim_per_group, tiles_per_group, n_tiles;   // 32-channel tiles never straddle a B/C group
+    int S, n_seg, n_work, nck;                     // segment length, #segments, #warp work items, #checkpoints
+    bool reverse, softplus;
+    const void *u, *delta, *z, *B, *C, *dout;
+    const float *A, *D, *delta_bias;
+    void *out, *out_z;
+    float *hstates;
+    int64_t u_bs, u_ds, delta_bs, delta_ds, z_bs, z_ds, out_bs, out_ds, out_z_bs, out_z_ds, dout_bs, dout_ds;
+    int64_t B_bs, B_gs, B_ns, B_ls, C_bs, C_gs, C_ns, C_ls;
+    float *P, *H, *hin, *cumP;                     // (batch, n_seg, N, dim) workspaces
+    // ---- backward only ----
+    void *du, *ddelta, *dz;
+    float *dA, *dB, *dC, *dD, *ddelta_bias;        // fp32 accumulators (zero-initialised by the caller)
+    int64_t du_bs, du_ds, ddelta_bs, ddelta_ds, dz_bs, dz_ds;
+    const float *hs;                               // forward states at every kCkpt-th position: (batch, *, N, dim)
+    int64_t hs_bs;                                 // batch stride of hs in floats
+    float *Pb, *Mloc, *Min;                        // (batch, nck, N, dim) reverse aggregates / carried adjoints
+};
+
+struct WorkItem {
+    int b, seg, g, d0, nrows;
+};
+
+// work item w -> (batch, segment, channel tile); tiles vary fastest so that warps working on the same
+// (batch, segment) -- and therefore the same B/C slab -- are co-scheduled.
+__device__ __forceinline__ WorkItem decode_work(const ScanP &p, int w) {
+    WorkItem wi;
+    const int tile = w % p.n_tiles;
+    const int rest = w / p.n_tiles;
+    wi.seg = rest % p.n_seg;
+    wi.b = rest / p.n_seg;
+    wi.g = tile / p.tiles_per_group;
+    const int tg = tile - wi.g * p.tiles_per_group;
+    wi.d0 = wi.g * p.dim_per_group + tg * 32;
+    wi.nrows = min(32, (wi.g + 1) * p.dim_per_group - wi.d0);
+    return wi;
+}
+
+// Segment length heuristic (host): largest S in {256..2048} that still yields >= 8 warps per SM on a
+// 148-SM B200; S divides 2048 so the reference's 2048-position chunk states fall on segment ends.
+inline int plan_segment(int batch, int n_tiles, int L) {
+    const long target = 148L * 8;
+    int S = 2048;
+    while (S > kCkpt && (long)batch * n_tiles * ((L + S - 1) / S) < target) S >>= 1;
+    return S;
+}
+
+cudaError_t scan_fwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, float *x, cudaStream_t st);
+cudaError_t scan_fwd_agg_dispatch(const ScanP &p, int dtype, int N, cudaStream_t st);
+cudaError_t scan_bwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, cudaStream_t st);
+cudaError_t carry_launch(const float *P, const float *H, float *hin, float *cumP, int batch, int n_seg, int N, int dim,
+                         int reverse_carry, cudaStream_t st);
+
+}  // namespace smb

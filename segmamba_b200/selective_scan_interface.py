@@ -1,0 +1,191 @@
+"""Autograd ops of the SegMamba hot path on top of the native library.
+
+Mirrors the reference's operator interface (same names, argument meaning and return conventions):
+
+* ``selective_scan_fn``            <- mamba/mamba_ssm/ops/selective_scan_interface.py:14-83  (SelectiveScanFn)
+* ``causal_conv1d_fn``             <- causal-conv1d/causal_conv1d/causal_conv1d_interface.py:10-46 (CausalConv1dFn)
+* ``mamba_inner_fn_no_out_proj``   <- selective_scan_interface.py:155-289,627-633 (MambaInnerFnNoOutProj)
+
+Differences that stay behind the interface: the native scan/conv kernels take a walk ``direction`` so the
+reversed pass of the tri-directional block needs no ``flip`` copies, the forward saves 256-position states
+instead of the pre-gate output so the backward neither re-reads ``out`` nor needs the 2048-chunk ``x``, and
+dB/dC come back already reduced over channels.  There is no CPU path: non-CUDA tensors raise RuntimeError.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch.amp import custom_bwd, custom_fwd
+
+from . import causal_conv1d_cuda, selective_scan_cuda
+
+
+class SelectiveScanFn(torch.autograd.Function):
+    """ssi.py:14-74."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+        if u.stride(-1) != 1:
+            u = u.contiguous()
+        if delta.stride(-1) != 1:
+            delta = delta.contiguous()
+        if D is not None:
+            D = D.contiguous()
+        if B.stride(-1) != 1:
+            B = B.contiguous()
+        if C.stride(-1) != 1:
+            C = C.contiguous()
+        if z is not None and z.stride(-1) != 1:
+            z = z.contiguous()
+        ctx.squeeze_B = B.dim() == 3
+        ctx.squeeze_C = C.dim() == 3
+        if ctx.squeeze_B:
+            B = B.unsqueeze(1)
+        if ctx.squeeze_C:
+            C = C.unsqueeze(1)
+        out, x, out_z, hst = selective_scan_cuda.fwd_ex(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
+                                                        want_out=z is None, want_x=return_last_state, want_hstates=True)
+        ctx.delta_softplus = delta_softplus
+        ctx.has_z = z is not None
+        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, hst)
+        res = out_z if ctx.has_z else out
+        if not return_last_state:
+            return res
+        last_state = x[:, :, -1, 1::2]          # (batch, dim, dstate)  ssi.py:40
+        return res, last_state
+
+    @staticmethod
+    def backward(ctx, dout, *args):
+        u, delta, A, B, C, D, z, delta_bias, hst = ctx.saved_tensors
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        du, ddelta, dA, dB, dC, dD, ddelta_bias, dz, _ = selective_scan_cuda.bwd_ex(
+            u, delta, A, B, C, D, z, delta_bias, dout, None, ctx.delta_softplus, False, hstates=hst)
+        dB = dB.to(B.dtype)
+        dC = dC.to(C.dtype)
+        dB = dB.squeeze(1) if ctx.squeeze_B else dB
+        dC = dC.squeeze(1) if ctx.squeeze_C else dC
+        return (du, ddelta, dA, dB, dC, dD if D is not None else None, dz,
+                ddelta_bias if delta_bias is not None else None, None, None)
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+    """if return_last_state is True, returns (out, last_state); last_state has shape (batch, dim, dstate)
+    and carries no gradient (ssi.py:77-83)."""
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+
+
+class CausalConv1dFn(torch.autograd.Function):
+    """causal_conv1d_interface.py:10-34."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias=None, activation=None):
+        if activation not in [None, "silu", "swish"]:
+            raise NotImplementedError("activation must be None, silu, or swish")
+        if x.stride(2) != 1:
+            x = x.contiguous()
+        bias = bias.contiguous() if bias is not None else None
+        ctx.save_for_backward(x, weight, bias)
+        ctx.activation = activation in ["silu", "swish"]
+        return causal_conv1d_cuda.causal_conv1d_fwd(x, weight, bias, ctx.activation)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, bias = ctx.saved_tensors
+        if dout.stride(2) != 1:
+            dout = dout.contiguous()
+        dx, dweight, dbias = causal_conv1d_cuda.causal_conv1d_bwd(x, weight, bias, dout, None, ctx.activation)
+        return dx, dweight, dbias if bias is not None else None, None
+
+
+def causal_conv1d_fn(x, weight, bias=None, activation=None):
+    """x: (batch, dim, seqlen); weight: (dim, width); bias: (dim,); activation: None | "silu" | "swish"."""
+    return CausalConv1dFn.apply(x, weight, bias, activation)
+
+
+class MambaInnerFnNoOutProj(torch.autograd.Function):
+    """conv1d+SiLU -> x_proj -> dt_proj -> selective scan -> SiLU(z) gate, with recompute in backward
+    (ssi.py:155-289, checkpoint_lvl=1).  ``direction`` = 1 walks L in descending order, which equals calling the
+    reference op on ``xz.flip(-1)`` and flipping its result back (mamba_simple.py:230,264)."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None, D=None,
+                delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True, direction=0):
+        if B is not None or C is not None or B_proj_bias is not None or C_proj_bias is not None:
+            raise RuntimeError("segmamba_b200: only input-dependent B and C without projection bias are supported "
+                               "(what Mamba.forward v3 passes, mamba_simple.py:217-260)")
+        if A.is_complex():
+            raise RuntimeError("segmamba_b200: complex A is out of scope")
+        L = xz.shape[-1]
+        delta_rank = delta_proj_weight.shape[1]
+        d_state = A.shape[-1]
+        if torch.is_autocast_enabled("cuda"):                                              # ssi.py:169-171
+            x_proj_weight = x_proj_weight.to(dtype=torch.get_autocast_dtype("cuda"))
+            delta_proj_weight = delta_proj_weight.to(dtype=torch.get_autocast_dtype("cuda"))
+        if xz.stride(-1) != 1:
+            xz = xz.contiguous()
+        conv1d_weight = conv1d_weight.reshape(conv1d_weight.shape[0], conv1d_weight.shape[-1])   # "d 1 w -> d w"
+        x, z = xz.chunk(2, dim=1)
+        conv1d_bias = conv1d_bias.contiguous() if conv1d_bias is not None else None
+        conv1d_out = causal_conv1d_cuda.causal_conv1d_fwd_ex(x, conv1d_weight, conv1d_bias, True, direction=direction)
+        bsz, d_inner, _ = conv1d_out.shape
+        x_dbl = F.linear(conv1d_out.permute(0, 2, 1).reshape(bsz * L, d_inner), x_proj_weight)          # (bl, R+2N)  :181
+        delta = (delta_proj_weight @ x_dbl[:, :delta_rank].t()).view(d_inner, bsz, L).permute(1, 0, 2)  # HBL   :182
+        Bm = x_dbl[:, delta_rank:delta_rank + d_state].view(bsz, L, d_state).permute(0, 2, 1).unsqueeze(1).contiguous()
+        Cm = x_dbl[:, -d_state:].view(bsz, L, d_state).permute(0, 2, 1).unsqueeze(1).contiguous()
+        D = D.contiguous() if D is not None else None
+        _, _, out_z, hst = selective_scan_cuda.fwd_ex(conv1d_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus,
+                                                      direction=direction, want_out=False, want_x=False, want_hstates=True)
+        ctx.delta_softplus = delta_softplus
+        ctx.direction = direction
+        ctx.save_for_backward(xz, conv1d_weight, conv1d_bias, x_dbl, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst)
+        return out_z
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        (xz, conv1d_weight, conv1d_bias, x_dbl, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst) = ctx.saved_tensors
+        L = xz.shape[-1]
+        delta_rank = delta_proj_weight.shape[1]
+        d_state = A.shape[-1]
+        direction = ctx.direction
+        x, z = xz.chunk(2, dim=1)
+        if dout.stride(-1) != 1:
+            dout = dout.contiguous()
+        # recompute conv1d_out and delta (ssi.py:238-241)
+        conv1d_out = causal_conv1d_cuda.causal_conv1d_fwd_ex(x, conv1d_weight, conv1d_bias, True, direction=direction)
+        bsz, d_inner, _ = conv1d_out.shape
+        delta = (delta_proj_weight @ x_dbl[:, :delta_rank].t()).view(d_inner, bsz, L).permute(1, 0, 2)
+        Bm = x_dbl[:, delta_rank:delta_rank + d_state].view(bsz, L, d_state).permute(0, 2, 1).unsqueeze(1).contiguous()
+        Cm = x_dbl[:, -d_state:].view(bsz, L, d_state).permute(0, 2, 1).unsqueeze(1).contiguous()
+        dxz = torch.empty_like(xz)                      # dx and dz are written next to each other (ssi.py:244-245)
+        dx, dz = dxz.chunk(2, dim=1)
+        dconv1d_out, ddelta, dA, dB, dC, dD, ddelta_bias, dz, _ = selective_scan_cuda.bwd_ex(
+            conv1d_out, delta, A, Bm, Cm, D, z, delta_bias, dout, dz, ctx.delta_softplus, False,
+            direction=direction, hstates=hst)
+        dx_dbl = torch.empty_like(x_dbl)
+        dx_dbl[:, delta_rank:delta_rank + d_state] = dB.squeeze(1).permute(0, 2, 1).reshape(bsz * L, d_state)   # :255-262
+        dx_dbl[:, -d_state:] = dC.squeeze(1).permute(0, 2, 1).reshape(bsz * L, d_state)                         # :264-271
+        ddelta2 = ddelta.permute(1, 0, 2).reshape(d_inner, bsz * L)                                             # :272
+        ddelta_proj_weight = ddelta2 @ x_dbl[:, :delta_rank]                                                    # :273
+        dx_dbl[:, :delta_rank] = ddelta2.t() @ delta_proj_weight                                                # :274
+        dconv2 = dconv1d_out.permute(1, 0, 2).reshape(d_inner, bsz * L)                                         # :275
+        conv2 = conv1d_out.permute(1, 0, 2).reshape(d_inner, bsz * L)
+        dx_proj_weight = dx_dbl.t() @ conv2.t()                                                                 # :276
+        dconv2 = torch.addmm(dconv2, x_proj_weight.t(), dx_dbl.t())                                             # :277
+        dconv1d_out = dconv2.view(d_inner, bsz, L).permute(1, 0, 2)                                             # :278
+        dx, dconv1d_weight, dconv1d_bias = causal_conv1d_cuda.causal_conv1d_bwd_ex(
+            x, conv1d_weight, conv1d_bias, dconv1d_out, dx, True, direction=direction)                          # :281-283
+        dconv1d_weight = dconv1d_weight.to(conv1d_weight.dtype).unsqueeze(1)                                    # "d w -> d 1 w"
+        dconv1d_bias = dconv1d_bias.to(conv1d_bias.dtype) if conv1d_bias is not None else None
+        return (dxz, dconv1d_weight, dconv1d_bias, dx_proj_weight, ddelta_proj_weight, dA, None, None,
+                dD if D is not None else None, ddelta_bias if delta_bias is not None else None, None, None, None, None)
+
+
+def mamba_inner_fn_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None,
+                               D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True,
+                               direction=0):
+    """ssi.py:627-633 plus the native ``direction`` extension (0 = the reference op)."""
+    return MambaInnerFnNoOutProj.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
+                                       delta_bias, B_proj_bias, C_proj_bias, delta_softplus, direction)
