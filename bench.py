@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SegMamba hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # native arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the oracle port on the host cores
+
+Metric (BASELINE.json): patches/sec, one patch = one 4x128^3 volume, forward + backward.
+Workload (config.workload): BASELINE.json configs[2] -- default SegMamba (depths [2,2,2,2], dims [48,96,192,384]) training
+step on synthetic 4x128^3 patches, batch 2 per GPU, bf16 autocast, CrossEntropy, SGD(nesterov) + grad-clip, DDP over NCCL
+for N > 1 (weak scaling).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "patches_per_sec_fwd_bwd_128cube_4ch"
+UNIT = "patches/s"
+PATCH = 128
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=2, help="patches per GPU per step (3_train.py:23)")
+    ap.add_argument("--patch", type=int, default=PATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--channels-last", action="store_true", help="channels_last_3d activations for the conv stack")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="edge of the cubic crop the CPU arm runs per step")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks / throttle reasons sampled DURING the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/) on the host cores.  One step = forward + backward of one cubic crop.
+# ----------------------------------------------------------------------------------------------
+def cpu_step_factory(sample: int):
+    import torch
+    from oracle import oracle as orc
+    from segmamba_b200.segmamba import SegMamba
+    orc.build()
+    orc.set_precision("f32")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = SegMamba(in_chans=4, out_chans=4, depths=[2, 2, 2, 2], feat_size=[48, 96, 192, 384])   # weights only
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
+    x = torch.rand(1, 4, sample, sample, sample)
+    y = torch.randint(0, 4, (1, sample, sample, sample))
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        logits = orc.segmamba_forward(sd, x)
+        loss = torch.nn.functional.cross_entropy(logits, y)
+        loss.backward()
+        return float(loss)
+
+    frac = (sample / PATCH) ** 3
+    desc = (f"oracle port (C scan/conv1d with OpenMP + torch CPU convs), fp32, one {sample}^3 crop forward+backward per step = "
+            f"{frac:.4g} of a 128^3 patch; value = {frac:.4g} / seconds")
+    return step, frac, cores, desc
+
+
+def run_cpu(steps: int, warmup: int, sample: int):
+    step, frac, cores, desc = cpu_step_factory(sample)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": frac / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds_per_step": dt}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = run_cpu(args.steps, args.warmup, args.cpu_sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "global_batch": 1, "note": "CPU arm: the reference has no CPU path for the "
+                   "model (Mamba.forward v3 is CUDA-only); this is the oracle port of it on the host cores"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return (f"SegMamba default (depths [2,2,2,2], dims [48,96,192,384]) training step on synthetic 4x{args.patch}^3 patches, "
+            f"batch {args.batch}/GPU, bf16 autocast, CE loss, SGD nesterov + clip (BASELINE.json configs[2])")
+
+
+# ----------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------
+def scan_fwd_bytes(meta):
+    """algorithmic HBM bytes of one fused-path scan forward call: reads u, delta, z, B, C once, writes out_z once and the
+    256-position states kept for backward (DESIGN.md 'Roofline')."""
+    batch, dim, L, N, s, has_z, has_out = meta
+    nck = (L + 255) // 256
+    streams = 2 + (2 if has_z else 1) + (1 if (has_out and has_z) else 0)
+    return s * batch * L * (streams * dim + 2 * N) + 4 * batch * (nck + 1) * N * dim + 4 * (dim * N + 2 * dim)
+
+
+def scan_bwd_bytes(meta):
+    """reads u, delta, z, dout, B, C, saved states; writes du, ddelta, dz and fp32 dB, dC."""
+    batch, dim, L, N, s, has_z, has_hs = meta
+    nck = (L + 255) // 256
+    streams = 3 + 2 + (2 if has_z else 0)
+    return s * batch * L * (streams * dim + 2 * N) + 2 * 4 * batch * N * L + 4 * batch * (nck + 1) * N * dim
+
+
+def main_native(args):
+    import torch
+    import torch.distributed as dist
+    from segmamba_b200 import _lib
+    from segmamba_b200.segmamba import SegMamba
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (native arm) needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=dev)
+    _lib.lib()   # fail loudly now if the native library is missing
+
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    model = SegMamba(in_chans=4, out_chans=4, depths=[2, 2, 2, 2], feat_size=[48, 96, 192, 384]).to(dev)
+    if args.channels_last:
+        model = model.to(memory_format=torch.channels_last_3d)
+    model.train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)   # 3_train.py:51-52
+    B, P = args.batch, args.patch
+    g = torch.Generator().manual_seed(42 + rank)                                                           # trainer.py:331
+    x_host = torch.rand(B, 4, P, P, P, generator=g).pin_memory()
+    y_host = torch.randint(0, 4, (B, P, P, P), generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    y_dev = y_host.to(dev)
+    loss_host = torch.zeros(1).pin_memory()
+    mf = torch.channels_last_3d if args.channels_last else torch.contiguous_format
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = net(x.contiguous(memory_format=mf))
+            loss = torch.nn.functional.cross_entropy(logits.float(), y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 12.0)                                           # trainer.py:464
+        opt.step()
+        return loss
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        loss = step(xd, yd)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step(x_dev, y_dev)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = _lib.launch_count()
+    sampler.start()
+    with _lib.profile() as prof:
+        total_ms = timed(lambda: step(x_dev, y_dev), args.steps)
+        durs = prof.durations()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        e2e_step()
+        e2e_ms = timed(e2e_step, args.steps) / args.steps
+        e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 8), "d2h_bytes_per_step": 4,
+               "ms_per_step": e2e_ms}
+
+    # ---- roofline of the dominant native launch: the stage-0 forward scan (largest L) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    def roof(op, bytes_fn):
+        metas = [m for (o, m) in durs if o == op]
+        if not metas:
+            return None
+        meta = max(metas, key=lambda m: m[2])            # largest L = stage 0
+        d = durs[(op, meta)]
+        ms = sum(d) / len(d)
+        by = bytes_fn(meta)
+        ach = by / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "kernel": f"smb_{op} (all passes) at batch={meta[0]} dim={meta[1]} L={meta[2]} N={meta[3]} elt={meta[4]}B",
+                "algorithmic_bytes": by, "avg_ms": ms, "launches_timed": len(d), "peak_source": peak_src}
+
+    roofline = roof("scan_fwd", scan_fwd_bytes)
+    roof_bwd = roof("scan_bwd", scan_bwd_bytes)
+    native_ms = {}
+    for (op, meta), d in durs.items():
+        native_ms[op] = native_ms.get(op, 0.0) + sum(d) / args.steps
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "inputs larger than L2: one step touches > 10 GB of activations (126 MB L2)",
+                       "channels_last_3d": bool(args.channels_last)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline,
+            "roofline_scan_bwd": roof_bwd,
+            "native_ms_per_step": native_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res = run_cpu(1, 0, args.cpu_sample)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_native(a)

@@ -60,6 +60,8 @@ enum { SMB_DIR_FORWARD = 0, SMB_DIR_REVERSE = 1 };
 
 SMB_API int smb_version(void);
 SMB_API const char *smb_last_error(void);
+/* number of CUDA kernels this library has launched in the calling process (monotonic; for bench accounting) */
+SMB_API uint64_t smb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Selective scan.

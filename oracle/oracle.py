@@ -29,6 +29,13 @@ import torch.nn.functional as F
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBS: dict[str, ctypes.CDLL] = {}
+_PRECISION = "f64"     # arithmetic of the autograd wrappers: "f64" = checker, "f32" = the timed CPU baseline
+
+
+def set_precision(p: str) -> None:
+    global _PRECISION
+    assert p in ("f64", "f32")
+    _PRECISION = p
 
 _fp = ctypes.POINTER(ctypes.c_float)
 
@@ -154,7 +161,7 @@ def causal_conv1d_bwd_raw(x, weight, bias, dout, silu=False, precision="f64"):
 class _SelectiveScanOracle(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus):
-        y, oz, _, _ = selective_scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus)
+        y, oz, _, _ = selective_scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, precision=_PRECISION)
         ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias)
         ctx.delta_softplus = delta_softplus
         return (oz if z is not None else y).to(u.dtype)
@@ -162,7 +169,7 @@ class _SelectiveScanOracle(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         u, delta, A, B, C, D, z, delta_bias = ctx.saved_tensors
-        g = selective_scan_bwd_raw(u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, dout)
+        g = selective_scan_bwd_raw(u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, dout, precision=_PRECISION)
         dB = g["dB"] if B.dim() == 4 else g["dB"].squeeze(1)
         dC = g["dC"] if C.dim() == 4 else g["dC"].squeeze(1)
         return (g["du"].to(u.dtype), g["ddelta"].to(delta.dtype), g["dA"], dB.to(B.dtype), dC.to(C.dtype),
@@ -181,12 +188,12 @@ class _CausalConv1dOracle(torch.autograd.Function):
     def forward(ctx, x, weight, bias, silu):
         ctx.save_for_backward(x, weight, bias)
         ctx.silu = silu
-        return causal_conv1d_fwd_raw(x, weight, bias, silu).to(x.dtype)
+        return causal_conv1d_fwd_raw(x, weight, bias, silu, precision=_PRECISION).to(x.dtype)
 
     @staticmethod
     def backward(ctx, dout):
         x, weight, bias = ctx.saved_tensors
-        dx, dw, db = causal_conv1d_bwd_raw(x, weight, bias, dout, ctx.silu)
+        dx, dw, db = causal_conv1d_bwd_raw(x, weight, bias, dout, ctx.silu, precision=_PRECISION)
         return dx.to(x.dtype), dw.to(weight.dtype), (db.to(bias.dtype) if bias is not None else None), None
 
 

@@ -72,6 +72,7 @@ class SeqPermuteArgs(ctypes.Structure):
 EXPORTS = {
     "smb_version": (ctypes.c_int, []),
     "smb_last_error": (ctypes.c_char_p, []),
+    "smb_launch_count": (ctypes.c_uint64, []),
     "smb_scan_fwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "smb_scan_fwd": (ctypes.c_int, [ctypes.POINTER(ScanFwdArgs), _vp]),
     "smb_scan_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
@@ -111,6 +112,51 @@ def lib() -> ctypes.CDLL:
                     fn.argtypes = args
                 _lib = l
     return _lib
+
+
+# ---- optional per-op device timing (bench.py's roofline leg).  Events are recorded on torch's current stream, which is
+# the stream the library's kernels are enqueued on (stream_ptr below). ----
+_PROF = None
+
+
+class profile:
+    """with _lib.profile() as prof: ...  ->  prof.durations() = {(op, meta): [ms, ...]} after a synchronize."""
+
+    def __enter__(self):
+        global _PROF
+        self.records = []
+        _PROF = self.records
+        return self
+
+    def __exit__(self, *exc):
+        global _PROF
+        _PROF = None
+        return False
+
+    def durations(self):
+        torch.cuda.synchronize()
+        out = {}
+        for op, meta, s, e in self.records:
+            out.setdefault((op, meta), []).append(s.elapsed_time(e))
+        return out
+
+
+def call(op: str, meta: tuple, fn, device) -> None:
+    """run one C-ABI call (returns its int code through check()); time it with CUDA events when profiling is on."""
+    if _PROF is None:
+        check(fn())
+        return
+    stream = torch.cuda.current_stream(device)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(stream)
+    rc = fn()
+    e.record(stream)
+    _PROF.append((op, meta, s, e))
+    check(rc)
+
+
+def launch_count() -> int:
+    return int(lib().smb_launch_count())
 
 
 def check(rc: int) -> None:

@@ -52,7 +52,8 @@ def causal_conv1d_fwd_ex(x, weight, bias_, silu_activation, *, direction=0, out=
         a.x_bs, a.x_ds = x.stride(0), x.stride(1)
         a.out_bs, a.out_ds = out.stride(0), out.stride(1)
         a.w_ds, a.w_ws = w32.stride(0), w32.stride(1)
-        _lib.check(_lib.lib().smb_conv1d_fwd(ctypes.byref(a), _lib.stream_ptr(dev)))
+        sp = _lib.stream_ptr(dev)
+        _lib.call("conv1d_fwd", (batch, dim, L, x.element_size()), lambda: _lib.lib().smb_conv1d_fwd(ctypes.byref(a), sp), dev)
     return out
 
 
@@ -89,7 +90,8 @@ def causal_conv1d_bwd_ex(x, weight, bias_, dout, dx_, silu_activation, *, direct
         a.dout_bs, a.dout_ds = dout.stride(0), dout.stride(1)
         a.dx_bs, a.dx_ds = dx.stride(0), dx.stride(1)
         a.w_ds, a.w_ws = w32.stride(0), w32.stride(1)
-        _lib.check(_lib.lib().smb_conv1d_bwd(ctypes.byref(a), _lib.stream_ptr(dev)))
+        sp = _lib.stream_ptr(dev)
+        _lib.call("conv1d_bwd", (batch, dim, L, x.element_size()), lambda: _lib.lib().smb_conv1d_bwd(ctypes.byref(a), sp), dev)
     return dx, dweight, dbias
 
 
@@ -127,5 +129,6 @@ def seq_permute(src, nslices, inverse=False, out=None, accumulate=False):
     a.src, a.dst = _lib.ptr(s2), _lib.ptr(out)
     a.src_rs, a.dst_rs = s2.stride(0), L
     with torch.cuda.device(src.device):
-        _lib.check(_lib.lib().smb_seq_permute(ctypes.byref(a), _lib.stream_ptr(src.device)))
+        sp = _lib.stream_ptr(src.device)
+        _lib.call("seq_permute", (int(s2.shape[0]), L, src.element_size()), lambda: _lib.lib().smb_seq_permute(ctypes.byref(a), sp), src.device)
     return out

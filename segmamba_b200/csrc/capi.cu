@@ -1,4 +1,5 @@
 // extern "C" entry points of libsegmamba_b200.so (see include/segmamba_b200.h).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -6,6 +7,11 @@
 #include "../../include/segmamba_b200.h"
 #include "conv_internal.h"
 #include "scan_internal.h"
+
+namespace smb {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace smb
 
 namespace {
 
@@ -57,6 +63,7 @@ extern "C" {
 
 SMB_API int smb_version(void) { return 100; }
 SMB_API const char *smb_last_error(void) { return g_err; }
+SMB_API uint64_t smb_launch_count(void) { return (uint64_t)smb::g_launches.load(std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------------------------
 SMB_API size_t smb_scan_fwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {

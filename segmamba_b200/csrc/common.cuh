@@ -8,6 +8,9 @@
 
 namespace smb {
 
+// host-side launch accounting (smb_launch_count)
+void count_launch();
+
 constexpr int kTile = 32;         // scan positions per warp-private shared-memory tile
 constexpr int kCkpt = 256;        // state checkpoint interval (scan positions) shared by fwd and bwd
 constexpr float kLog2e = 1.4426950408889634f;

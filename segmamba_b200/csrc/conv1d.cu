@@ -206,6 +206,7 @@ static cudaError_t conv_launch_t(const ConvP &p, bool bwd, cudaStream_t st) {
     dim3 grid((p.L + per_block - 1) / per_block, p.dim, p.batch);
     if (!bwd) conv1d_fwd_kernel<T><<<grid, kConvThreads, 0, st>>>(p);
     else conv1d_bwd_kernel<T><<<grid, kConvThreads, 0, st>>>(p);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -225,7 +226,7 @@ static cudaError_t permute_launch_t(const void *src, void *dst, int64_t src_rs, 
     const int nr = inverse ? Lp : ns, nc = inverse ? ns : Lp;
     dim3 grid((nc + 31) / 32, (nr + 31) / 32, rows);
     seq_permute_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T *>(src), reinterpret_cast<T *>(dst), src_rs, dst_rs,
-                                                nr, nc, accumulate);
+                                                nr, nc, accumulate); count_launch();
     return cudaGetLastError();
 }
 

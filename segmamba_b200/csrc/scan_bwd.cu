@@ -345,7 +345,7 @@ static cudaError_t launch_bwd(const ScanP &p, cudaStream_t st) {
     const int ctas = (p.n_work + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t sm1 = (size_t)kWarpsPerCta * (3 * kTile * kTile + kTile * N) * sizeof(float);
     if ((e = cudaFuncSetAttribute(scan_bwd_ragg_kernel<T, N, kHasZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
-    scan_bwd_ragg_kernel<T, N, kHasZ><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p);
+    scan_bwd_ragg_kernel<T, N, kHasZ><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
     // R2
     if ((e = carry_launch(p.Pb, p.Mloc, p.Min, nullptr, p.batch, p.nck, N, p.dim, 1, st)) != cudaSuccess) return e;
     // R3
@@ -353,7 +353,7 @@ static cudaError_t launch_bwd(const ScanP &p, cudaStream_t st) {
     if ((e = cudaFuncSetAttribute(scan_bwd_main_kernel<T, N, kHasZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
     const int octs = ((p.dim_per_group + kBwdWarps - 1) / kBwdWarps) * p.G;
     dim3 grid(p.nck, octs, p.batch);
-    scan_bwd_main_kernel<T, N, kHasZ><<<grid, kBwdWarps * 32, sm3, st>>>(p);
+    scan_bwd_main_kernel<T, N, kHasZ><<<grid, kBwdWarps * 32, sm3, st>>>(p); count_launch();
     return cudaGetLastError();
 }
 

@@ -306,29 +306,29 @@ static cudaError_t launch_fwd(const ScanP &p, bool has_z, float *x, cudaStream_t
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(scan_fwd_agg_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
     if (p.n_seg > 1) {
-        scan_fwd_agg_kernel<T, N><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p);
+        scan_fwd_agg_kernel<T, N><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
         dim3 cg((p.dim + 31) / 32, N, p.batch);
-        carry_kernel<<<cg, 1024, 0, st>>>(p.P, p.H, p.hin, x ? p.cumP : nullptr, p.n_seg, N, p.dim, 0);
+        carry_kernel<<<cg, 1024, 0, st>>>(p.P, p.H, p.hin, x ? p.cumP : nullptr, p.n_seg, N, p.dim, 0); count_launch();
     } else {
         // single segment: incoming state is zero; cumP (only for x) still needs pass 1
         if ((e = cudaMemsetAsync(p.hin, 0, sizeof(float) * (size_t)p.batch * N * p.dim, st)) != cudaSuccess) return e;
         if (x) {
-            scan_fwd_agg_kernel<T, N><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p);
+            scan_fwd_agg_kernel<T, N><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
             if ((e = cudaMemcpyAsync(p.cumP, p.P, sizeof(float) * (size_t)p.batch * N * p.dim, cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
         }
     }
     if (has_z) {
         if ((e = cudaFuncSetAttribute(scan_fwd_main_kernel<T, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
-        scan_fwd_main_kernel<T, N, true><<<ctas, kWarpsPerCta * 32, sm3, st>>>(p);
+        scan_fwd_main_kernel<T, N, true><<<ctas, kWarpsPerCta * 32, sm3, st>>>(p); count_launch();
     } else {
         if ((e = cudaFuncSetAttribute(scan_fwd_main_kernel<T, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
-        scan_fwd_main_kernel<T, N, false><<<ctas, kWarpsPerCta * 32, sm3, st>>>(p);
+        scan_fwd_main_kernel<T, N, false><<<ctas, kWarpsPerCta * 32, sm3, st>>>(p); count_launch();
     }
     if (x) {
         const int n_chunks = (p.L + 2047) / 2048;
         const int64_t total = (int64_t)p.batch * p.dim * n_chunks * N;
         x_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.hstates, p.cumP, x, p.batch, p.dim, N, p.L, p.S,
-                                                                          p.n_seg, p.nck, n_chunks);
+                                                                          p.n_seg, p.nck, n_chunks); count_launch();
     }
     return cudaGetLastError();
 }
@@ -354,7 +354,7 @@ static cudaError_t launch_agg_only(const ScanP &p, cudaStream_t st) {
     const size_t sm1 = (size_t)kWarpsPerCta * (2 * kTile * kTile + kTile * N) * sizeof(float);
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(scan_fwd_agg_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
-    scan_fwd_agg_kernel<T, N><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p);
+    scan_fwd_agg_kernel<T, N><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
     return cudaGetLastError();
 }
 
@@ -371,7 +371,7 @@ cudaError_t scan_fwd_agg_dispatch(const ScanP &p, int dtype, int N, cudaStream_t
 cudaError_t carry_launch(const float *P, const float *H, float *hin, float *cumP, int batch, int n_seg, int N, int dim,
                          int reverse_carry, cudaStream_t st) {
     dim3 cg((dim + 31) / 32, N, batch);
-    carry_kernel<<<cg, 1024, 0, st>>>(P, H, hin, cumP, n_seg, N, dim, reverse_carry);
+    carry_kernel<<<cg, 1024, 0, st>>>(P, H, hin, cumP, n_seg, N, dim, reverse_carry); count_launch();
     return cudaGetLastError();
 }
 

@@ -96,7 +96,8 @@ def fwd_ex(u, delta, A, B, C, D_=None, z_=None, delta_bias_=None, delta_softplus
         a.B_bs, a.B_gs, a.B_ns, a.B_ls = B.stride(0), B.stride(1), B.stride(2), B.stride(3)
         a.C_bs, a.C_gs, a.C_ns, a.C_ls = C.stride(0), C.stride(1), C.stride(2), C.stride(3)
         a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
-        _lib.check(l.smb_scan_fwd(ctypes.byref(a), _lib.stream_ptr(dev)))
+        sp = _lib.stream_ptr(dev)
+        _lib.call("scan_fwd", (batch, dim, L, N, u.element_size(), has_z, out is not None), lambda: l.smb_scan_fwd(ctypes.byref(a), sp), dev)
     return out, x, out_z, hst
 
 
@@ -161,7 +162,8 @@ def bwd_ex(u, delta, A, B, C, D_, z_, delta_bias_, dout, dz_=None, delta_softplu
         a.B_bs, a.B_gs, a.B_ns, a.B_ls = B.stride(0), B.stride(1), B.stride(2), B.stride(3)
         a.C_bs, a.C_gs, a.C_ns, a.C_ls = C.stride(0), C.stride(1), C.stride(2), C.stride(3)
         a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
-        _lib.check(l.smb_scan_bwd(ctypes.byref(a), _lib.stream_ptr(dev)))
+        sp = _lib.stream_ptr(dev)
+        _lib.call("scan_bwd", (batch, dim, L, N, u.element_size(), has_z, hstates is not None), lambda: l.smb_scan_bwd(ctypes.byref(a), sp), dev)
     return du, ddelta, dA, dB, dC, dD, dbias, dz, out_z
 
 

@@ -90,7 +90,9 @@ def test_segmamba_vs_reference_golden():
     grads = torch.autograd.grad(out, [p for _, p in m.named_parameters()], dout)
     norms = np.array([float(g.double().norm()) for g in grads])
     ref_norms = gold["grad_norms"]
-    bad = [(n, a, b) for n, a, b in zip(names, norms, ref_norms) if abs(a - b) > 5e-3 * max(b, 1e-6) + 1e-7]
+    # conv biases that feed an InstanceNorm have an analytically zero gradient: compare against the global scale
+    floor = 1e-4 * float(ref_norms.max())
+    bad = [(n, a, b) for n, a, b in zip(names, norms, ref_norms) if abs(a - b) > 5e-3 * b + floor]
     assert not bad, f"grad norm mismatch: {bad[:5]}"
     for n, g in zip(names, grads):
         if "grad." + n in gold.files:
