@@ -134,20 +134,20 @@ ORC_API void orc_selective_scan_bwd(
     if (dC) memset(dC, 0, sizeof(float) * bc_elems);
     if (dD) memset(dD, 0, sizeof(float) * (size_t)dim);
     if (ddelta_bias) memset(ddelta_bias, 0, sizeof(float) * (size_t)dim);
-    /* double accumulators for the cross-row reductions, to stay deterministic under OpenMP we
-     * parallelise over channels d and loop batch inside (dB/dC need a group-level reduction:
-     * done with per-thread serialisation over groups below). */
+    /* double accumulators for the cross-channel reductions; channels run in parallel under OpenMP and
+     * add into dB/dC with atomics (summation order varies at the 1e-16 level only). */
     double *dBacc = dB ? (double *)calloc(bc_elems, sizeof(double)) : NULL;
     double *dCacc = dC ? (double *)calloc(bc_elems, sizeof(double)) : NULL;
     const int dpg = dim / G;
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int g = 0; g < G; ++g) {
+    for (int d = 0; d < dim; ++d) {
+        const int g = d / dpg;
         real_t *hs = (real_t *)malloc(sizeof(real_t) * (size_t)L * N);   /* h_t,n           */
         real_t *as = (real_t *)malloc(sizeof(real_t) * (size_t)L * N);   /* a_t,n           */
         real_t *dts = (real_t *)malloc(sizeof(real_t) * (size_t)L);      /* softplus'd delta */
         real_t *gs = (real_t *)malloc(sizeof(real_t) * (size_t)L);       /* grad wrt y      */
         real_t *lam = (real_t *)malloc(sizeof(real_t) * (size_t)N);
-        for (int d = g * dpg; d < (g + 1) * dpg; ++d) {
+        {
             double dA_acc[256]; for (int n = 0; n < N; ++n) dA_acc[n] = 0;
             double dD_acc = 0, dbias_acc = 0;
             for (int b = 0; b < batch; ++b) {
@@ -198,8 +198,16 @@ ORC_API void orc_selective_scan_bwd(
                         du_t += l * Bv * dt;                             /* :280-281          */
                         ddt += l * Bv * uv + l * (real_t)A[d * N + n] * hm;   /* :282-283     */
                         dA_acc[n] += (double)(l * dt * hm);              /* :284              */
-                        if (dBacc) dBacc[(((size_t)b * G + g) * N + n) * L + t] += (double)(l * dt * uv);   /* :292 */
-                        if (dCacc) dCacc[(((size_t)b * G + g) * N + n) * L + t] += (double)(gy * h);        /* :294 */
+                        if (dBacc) {
+                            const double v = (double)(l * dt * uv);                                         /* :292 */
+#pragma omp atomic
+                            dBacc[(((size_t)b * G + g) * N + n) * L + t] += v;
+                        }
+                        if (dCacc) {
+                            const double v = (double)(gy * h);                                              /* :294 */
+#pragma omp atomic
+                            dCacc[(((size_t)b * G + g) * N + n) * L + t] += v;
+                        }
                     }
                     if (du) du[row * L + t] = (float)du_t;
                     /* through softplus (bwd_kernel.cuh:439-453) */

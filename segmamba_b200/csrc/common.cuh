@@ -11,6 +11,19 @@ namespace smb {
 // host-side launch accounting (smb_launch_count)
 void count_launch();
 
+// opt a kernel into > 48 KB dynamic shared memory once per device (the attribute is per context)
+#define SMB_SET_SMEM_ONCE(kernel, bytes)                                                                        \
+    do {                                                                                                        \
+        static bool done_[64] = {};                                                                             \
+        int dv_ = 0;                                                                                            \
+        cudaGetDevice(&dv_);                                                                                    \
+        if (!done_[dv_ & 63]) {                                                                                 \
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));       \
+            if (e != cudaSuccess) return e;                                                                     \
+            done_[dv_ & 63] = true;                                                                             \
+        }                                                                                                       \
+    } while (0)
+
 constexpr int kTile = 32;         // scan positions per warp-private shared-memory tile
 constexpr int kCkpt = 256;        // state checkpoint interval (scan positions) shared by fwd and bwd
 constexpr float kLog2e = 1.4426950408889634f;

@@ -344,13 +344,13 @@ static cudaError_t launch_bwd(const ScanP &p, cudaStream_t st) {
     // R1
     const int ctas = (p.n_work + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t sm1 = (size_t)kWarpsPerCta * (3 * kTile * kTile + kTile * N) * sizeof(float);
-    if ((e = cudaFuncSetAttribute(scan_bwd_ragg_kernel<T, N, kHasZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
+    SMB_SET_SMEM_ONCE((scan_bwd_ragg_kernel<T, N, kHasZ>), sm1);
     scan_bwd_ragg_kernel<T, N, kHasZ><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
     // R2
     if ((e = carry_launch(p.Pb, p.Mloc, p.Min, nullptr, p.batch, p.nck, N, p.dim, 1, st)) != cudaSuccess) return e;
     // R3
     const size_t sm3 = (size_t)(2 * N + 2 * kBwdWarps) * kRowPad * sizeof(float);
-    if ((e = cudaFuncSetAttribute(scan_bwd_main_kernel<T, N, kHasZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
+    SMB_SET_SMEM_ONCE((scan_bwd_main_kernel<T, N, kHasZ>), sm3);
     const int octs = ((p.dim_per_group + kBwdWarps - 1) / kBwdWarps) * p.G;
     dim3 grid(p.nck, octs, p.batch);
     scan_bwd_main_kernel<T, N, kHasZ><<<grid, kBwdWarps * 32, sm3, st>>>(p); count_launch();

@@ -304,7 +304,7 @@ static cudaError_t launch_fwd(const ScanP &p, bool has_z, float *x, cudaStream_t
     const size_t sm1 = (size_t)kWarpsPerCta * (2 * kTile * kTile + kTile * N) * sizeof(float);
     const size_t sm3 = (size_t)kWarpsPerCta * (3 * kTile * kTile + 2 * kTile * N) * sizeof(float);
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(scan_fwd_agg_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
+    SMB_SET_SMEM_ONCE((scan_fwd_agg_kernel<T, N>), sm1);
     if (p.n_seg > 1) {
         scan_fwd_agg_kernel<T, N><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
         dim3 cg((p.dim + 31) / 32, N, p.batch);
@@ -318,10 +318,10 @@ static cudaError_t launch_fwd(const ScanP &p, bool has_z, float *x, cudaStream_t
         }
     }
     if (has_z) {
-        if ((e = cudaFuncSetAttribute(scan_fwd_main_kernel<T, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
+        SMB_SET_SMEM_ONCE((scan_fwd_main_kernel<T, N, true>), sm3);
         scan_fwd_main_kernel<T, N, true><<<ctas, kWarpsPerCta * 32, sm3, st>>>(p); count_launch();
     } else {
-        if ((e = cudaFuncSetAttribute(scan_fwd_main_kernel<T, N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)) != cudaSuccess) return e;
+        SMB_SET_SMEM_ONCE((scan_fwd_main_kernel<T, N, false>), sm3);
         scan_fwd_main_kernel<T, N, false><<<ctas, kWarpsPerCta * 32, sm3, st>>>(p); count_launch();
     }
     if (x) {
@@ -353,7 +353,7 @@ static cudaError_t launch_agg_only(const ScanP &p, cudaStream_t st) {
     const int ctas = (p.n_work + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t sm1 = (size_t)kWarpsPerCta * (2 * kTile * kTile + kTile * N) * sizeof(float);
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(scan_fwd_agg_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)) != cudaSuccess) return e;
+    SMB_SET_SMEM_ONCE((scan_fwd_agg_kernel<T, N>), sm1);
     scan_fwd_agg_kernel<T, N><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
     return cudaGetLastError();
 }

