@@ -12,8 +12,8 @@
  *   smb_scan_bwd      selective_scan_cuda.bwd   mamba/csrc/selective_scan/selective_scan.cpp:338-492
  *   smb_conv1d_fwd    causal_conv1d_cuda.causal_conv1d_fwd   causal-conv1d/csrc/causal_conv1d.cpp:130-189
  *   smb_conv1d_bwd    causal_conv1d_cuda.causal_conv1d_bwd   causal-conv1d/csrc/causal_conv1d.cpp:191-268
- *   smb_inner_*       the fused body of MambaInnerFnNoOutProj.forward/backward,
- *                     mamba/mamba_ssm/ops/selective_scan_interface.py:159-289
+ *   smb_instnorm_*    nn.InstanceNorm3d + activation + residual chains of GSC / UnetResBlock,
+ *                     model_segmamba/segmamba.py:111-130, monai/networks/blocks/dynunet_block.py:98-111
  *   smb_seq_permute   the flip / inter-slice re-orderings of Mamba.forward (v3),
  *                     mamba/mamba_ssm/modules/mamba_simple.py:230-261
  *
@@ -172,6 +172,53 @@ typedef struct smb_seq_permute_args {
 } smb_seq_permute_args;
 
 SMB_API int smb_seq_permute(const smb_seq_permute_args *args, void *cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused InstanceNorm3d(affine=False) [+ second operand] [+ ReLU / LeakyReLU] on channels-last activations
+ * viewed as (batch, spatial, channels), channels contiguous.  Replaces the reference's chains of
+ * nn.InstanceNorm3d + activation + residual add (model_segmamba/segmamba.py:111-130,147,171;
+ * monai/networks/blocks/dynunet_block.py:98-111):
+ *     y = act( IN(x) )                      mode2 = 0
+ *     y = act( IN(x) + x2 )                 mode2 = 1   (raw residual)
+ *     y = act( IN(x) + IN(x2) )             mode2 = 2   (both operands normalised with their own statistics)
+ * channels must be a multiple of 16 / sizeof(element).  stats / stats2: (batch, channels, 2) fp32 = (mean, rstd),
+ * written by the forward and read by the backward.  The backward returns dx and, for mode2 != 0, dx2.
+ * ---------------------------------------------------------------------------------------------- */
+enum { SMB_ACT_NONE = 0, SMB_ACT_RELU = 1, SMB_ACT_LEAKY_RELU = 2 };
+
+typedef struct smb_instnorm_args {
+    int32_t batch, channels;
+    int32_t dtype;
+    int32_t act;                /* SMB_ACT_* */
+    int32_t mode2;              /* 0, 1, 2 (see above) */
+    float slope;                /* LeakyReLU negative slope */
+    float eps;
+    int64_t spatial;
+    const void *x, *x2;         /* x2 may be NULL when mode2 == 0 */
+    void *y;
+    float *stats, *stats2;      /* stats2 may be NULL unless mode2 == 2 */
+    void *workspace;
+    size_t workspace_bytes;     /* >= smb_instnorm_workspace_bytes(...) */
+} smb_instnorm_args;
+
+typedef struct smb_instnorm_bwd_args {
+    int32_t batch, channels;
+    int32_t dtype;
+    int32_t act;
+    int32_t mode2;
+    float slope;
+    float eps;
+    int64_t spatial;
+    const void *x, *x2, *dy;
+    const float *stats, *stats2;
+    void *dx, *dx2;             /* dx2 may be NULL when the second operand needs no gradient */
+    void *workspace;
+    size_t workspace_bytes;
+} smb_instnorm_bwd_args;
+
+SMB_API size_t smb_instnorm_workspace_bytes(int32_t batch, int32_t channels, int64_t spatial, int32_t dtype);
+SMB_API int smb_instnorm_fwd(const smb_instnorm_args *args, void *cuda_stream);
+SMB_API int smb_instnorm_bwd(const smb_instnorm_bwd_args *args, void *cuda_stream);
 
 #ifdef __cplusplus
 }

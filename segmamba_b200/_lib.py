@@ -68,6 +68,24 @@ class SeqPermuteArgs(ctypes.Structure):
     )
 
 
+class InstNormArgs(ctypes.Structure):
+    _fields_ = (
+        [(n, _i32) for n in ("batch", "channels", "dtype", "act", "mode2")]
+        + [("slope", ctypes.c_float), ("eps", ctypes.c_float), ("spatial", _i64)]
+        + [(n, _vp) for n in ("x", "x2", "y", "stats", "stats2", "workspace")]
+        + [("workspace_bytes", _sz)]
+    )
+
+
+class InstNormBwdArgs(ctypes.Structure):
+    _fields_ = (
+        [(n, _i32) for n in ("batch", "channels", "dtype", "act", "mode2")]
+        + [("slope", ctypes.c_float), ("eps", ctypes.c_float), ("spatial", _i64)]
+        + [(n, _vp) for n in ("x", "x2", "dy", "stats", "stats2", "dx", "dx2", "workspace")]
+        + [("workspace_bytes", _sz)]
+    )
+
+
 # every symbol include/segmamba_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = {
     "smb_version": (ctypes.c_int, []),
@@ -80,6 +98,9 @@ EXPORTS = {
     "smb_conv1d_fwd": (ctypes.c_int, [ctypes.POINTER(Conv1dArgs), _vp]),
     "smb_conv1d_bwd": (ctypes.c_int, [ctypes.POINTER(Conv1dBwdArgs), _vp]),
     "smb_seq_permute": (ctypes.c_int, [ctypes.POINTER(SeqPermuteArgs), _vp]),
+    "smb_instnorm_workspace_bytes": (_sz, [_i32, _i32, _i64, _i32]),
+    "smb_instnorm_fwd": (ctypes.c_int, [ctypes.POINTER(InstNormArgs), _vp]),
+    "smb_instnorm_bwd": (ctypes.c_int, [ctypes.POINTER(InstNormBwdArgs), _vp]),
 }
 
 _lib = None

@@ -6,6 +6,7 @@
 
 #include "../../include/segmamba_b200.h"
 #include "conv_internal.h"
+#include "norm_internal.h"
 #include "scan_internal.h"
 
 namespace smb {
@@ -234,6 +235,73 @@ SMB_API int smb_seq_permute(const smb_seq_permute_args *a, void *cuda_stream) {
     cudaError_t e = smb::seq_permute_dispatch(a->src, a->dst, a->src_rs, a->dst_rs, a->rows, a->seqlen, a->nslices, a->inverse,
                                               a->accumulate, a->dtype, (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return cuda_fail(e, "smb_seq_permute");
+    return SMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int norm_common(int batch, int channels, int64_t spatial, int dtype, int act, int mode2, const char *who) {
+    if (batch <= 0 || channels <= 0 || spatial <= 0) return fail(SMB_EINVAL, "%s: batch, channels, spatial must be positive", who);
+    if (dtype < SMB_F32 || dtype > SMB_BF16) return fail(SMB_EINVAL, "%s: bad dtype %d", who, dtype);
+    const int V = dtype == SMB_F32 ? 4 : 8;
+    if (channels % V != 0) return fail(SMB_EUNSUPPORTED, "%s: channels %d must be a multiple of %d for this dtype", who, channels, V);
+    if (channels / V > 256) return fail(SMB_EUNSUPPORTED, "%s: channels %d too large", who, channels);
+    if (act < 0 || act > 2 || mode2 < 0 || mode2 > 2) return fail(SMB_EINVAL, "%s: bad act / mode2", who);
+    if (batch > 65535) return fail(SMB_EINVAL, "%s: batch limited to 65535", who);
+    return SMB_OK;
+}
+
+SMB_API size_t smb_instnorm_workspace_bytes(int32_t batch, int32_t channels, int64_t spatial, int32_t dtype) {
+    int n_cta = 0;
+    int64_t rows = 0;
+    const int eb = dtype == SMB_F32 ? 4 : 2;
+    if (batch <= 0 || channels <= 0 || spatial <= 0 || channels % (16 / eb) != 0) return 0;
+    smb::norm_plan(batch, channels, spatial, eb, &n_cta, &rows);
+    return sizeof(float) * ((size_t)2 * batch * n_cta * 3 * channels + (size_t)batch * channels * 3 + 64);
+}
+
+static void norm_fill(smb::NormP &p, int batch, int channels, int64_t spatial, int dtype, int act, int mode2, float slope, float eps,
+                      void *workspace) {
+    memset(&p, 0, sizeof(p));
+    p.batch = batch; p.channels = channels; p.spatial = spatial; p.act = act; p.mode2 = mode2; p.slope = slope; p.eps = eps;
+    smb::norm_plan(batch, channels, spatial, dtype == SMB_F32 ? 4 : 2, &p.n_cta, &p.rows_per_cta);
+    p.partial = reinterpret_cast<float *>(workspace);
+    p.sums = p.partial + (size_t)2 * batch * p.n_cta * 3 * channels;
+}
+
+SMB_API int smb_instnorm_fwd(const smb_instnorm_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_instnorm_fwd: null args");
+    int rc = norm_common(a->batch, a->channels, a->spatial, a->dtype, a->act, a->mode2, "smb_instnorm_fwd");
+    if (rc) return rc;
+    if (!a->x || !a->y || !a->stats) return fail(SMB_EINVAL, "smb_instnorm_fwd: x, y, stats are required");
+    if (a->mode2 && !a->x2) return fail(SMB_EINVAL, "smb_instnorm_fwd: x2 is required when mode2 != 0");
+    if (a->mode2 == 2 && !a->stats2) return fail(SMB_EINVAL, "smb_instnorm_fwd: stats2 is required when mode2 == 2");
+    const size_t need = smb_instnorm_workspace_bytes(a->batch, a->channels, a->spatial, a->dtype);
+    if (!a->workspace || a->workspace_bytes < need)
+        return fail(SMB_EWORKSPACE, "smb_instnorm_fwd: workspace of %zu bytes required, got %zu", need, a->workspace_bytes);
+    smb::NormP p;
+    norm_fill(p, a->batch, a->channels, a->spatial, a->dtype, a->act, a->mode2, a->slope, a->eps, a->workspace);
+    p.x = a->x; p.x2 = a->x2; p.y = a->y; p.stats = a->stats; p.stats2 = a->stats2;
+    cudaError_t e = smb::instnorm_dispatch(p, a->dtype, false, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_instnorm_fwd");
+    return SMB_OK;
+}
+
+SMB_API int smb_instnorm_bwd(const smb_instnorm_bwd_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_instnorm_bwd: null args");
+    int rc = norm_common(a->batch, a->channels, a->spatial, a->dtype, a->act, a->mode2, "smb_instnorm_bwd");
+    if (rc) return rc;
+    if (!a->x || !a->dy || !a->dx || !a->stats) return fail(SMB_EINVAL, "smb_instnorm_bwd: x, dy, dx, stats are required");
+    if (a->mode2 && !a->x2) return fail(SMB_EINVAL, "smb_instnorm_bwd: x2 is required when mode2 != 0");
+    if (a->mode2 == 2 && !a->stats2) return fail(SMB_EINVAL, "smb_instnorm_bwd: stats2 is required when mode2 == 2");
+    const size_t need = smb_instnorm_workspace_bytes(a->batch, a->channels, a->spatial, a->dtype);
+    if (!a->workspace || a->workspace_bytes < need)
+        return fail(SMB_EWORKSPACE, "smb_instnorm_bwd: workspace of %zu bytes required, got %zu", need, a->workspace_bytes);
+    smb::NormP p;
+    norm_fill(p, a->batch, a->channels, a->spatial, a->dtype, a->act, a->mode2, a->slope, a->eps, a->workspace);
+    p.x = a->x; p.x2 = a->x2; p.dy = a->dy; p.dx = a->dx; p.dx2 = a->dx2;
+    p.stats = const_cast<float *>(a->stats); p.stats2 = const_cast<float *>(a->stats2);
+    cudaError_t e = smb::instnorm_dispatch(p, a->dtype, true, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_instnorm_bwd");
     return SMB_OK;
 }
 

@@ -1,0 +1,396 @@
+// Fused InstanceNorm3d (+ optional second operand, + ReLU / LeakyReLU) forward / backward for sm_100a,
+// on channels-last activations viewed as (batch, spatial, channels).
+//
+// Replaces the reference's nn.InstanceNorm3d(affine=False, eps=1e-5) + activation + residual-add chains:
+//   GSC            ReLU(IN(conv(x)))                                   model_segmamba/segmamba.py:111-130
+//   UnetResBlock   LReLU(IN(conv1)),  LReLU(IN(conv2) + IN(conv3(res))) or LReLU(IN(conv2) + res)
+//                                                                      monai/networks/blocks/dynunet_block.py:98-111
+//   downsample / norm{i}   IN(x)                                       segmamba.py:147,171
+// which the reference runs as ATen batch_norm kernels in fp32 plus separate elementwise kernels (38 % of its
+// training step on B200, profiles/r1_launches_train_step_v1.csv).  These are pure HBM streaming ops:
+//   forward : 1 read for the statistics + 1 read + 1 write for the apply     (per operand)
+//   backward: reads dy, x (, x2) twice (sums, then apply), writes dx (, dx2)
+// Mapping: a CTA owns a contiguous range of rows (voxels); thread (r, cv) owns the 16-byte column vector cv of
+// rows r, r+RB, ...; so every global access is a full coalesced row segment and per-channel statistics live in
+// registers.  Variance uses per-CTA centred sums merged with Chan's formula (no E[x^2]-E[x]^2 cancellation
+// across the 2 M-voxel reduction).
+#include "norm_internal.h"
+
+namespace smb {
+
+constexpr int kNormThreads = 256;
+
+template <typename T> struct VecOf { static constexpr int V = 16 / sizeof(T); };
+
+template <typename T, int V> __device__ __forceinline__ void loadv(const T *p, float v[V]);
+template <> __device__ __forceinline__ void loadv<float, 4>(const float *p, float v[4]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+template <> __device__ __forceinline__ void loadv<__half, 8>(const __half *p, float v[8]) {
+    const float4 a = load4<__half>(p), b = load4<__half>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void loadv<__nv_bfloat16, 8>(const __nv_bfloat16 *p, float v[8]) {
+    const uint4 r = *reinterpret_cast<const uint4 *>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // bf16 -> fp32 is a 16-bit shift
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+template <typename T, int V> __device__ __forceinline__ void storev(T *p, const float v[V]);
+template <> __device__ __forceinline__ void storev<float, 4>(float *p, const float v[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void storev<__half, 8>(__half *p, const float v[8]) {
+    store4<__half>(p, make_float4(v[0], v[1], v[2], v[3]));
+    store4<__half>(p + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+template <> __device__ __forceinline__ void storev<__nv_bfloat16, 8>(__nv_bfloat16 *p, const float v[8]) {
+    uint4 r;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    r.x = *reinterpret_cast<uint32_t *>(&a); r.y = *reinterpret_cast<uint32_t *>(&b);
+    r.z = *reinterpret_cast<uint32_t *>(&c); r.w = *reinterpret_cast<uint32_t *>(&d);
+    *reinterpret_cast<uint4 *>(p) = r;
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+    if (act == 1) return v > 0.f ? v : 0.f;
+    if (act == 2) return v > 0.f ? v : slope * v;
+    return v;
+}
+__device__ __forceinline__ float act_grad(float v, int act, float slope) {
+    if (act == 1) return v > 0.f ? 1.f : 0.f;
+    if (act == 2) return v > 0.f ? 1.f : slope;
+    return 1.f;
+}
+
+struct RowMap {
+    int cv, r, RB;
+    int64_t row_lo, row_hi;
+    bool active;
+};
+// thread -> (column vector, first row, row step) for the CTA's row range
+__device__ __forceinline__ RowMap row_map(const NormP &p, int CV) {
+    RowMap m;
+    m.RB = kNormThreads / CV;
+    m.cv = threadIdx.x % CV;
+    m.r = threadIdx.x / CV;
+    m.active = m.r < m.RB;
+    m.row_lo = (int64_t)blockIdx.x * p.rows_per_cta;
+    m.row_hi = min(p.spatial, m.row_lo + p.rows_per_cta);
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward statistics: per-CTA (count, mean, M2) per channel, for x and optionally x2
+// partial layout: [which][batch][cta][3][C]
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool kTwo>
+__global__ void __launch_bounds__(kNormThreads) in_stats_fwd_kernel(const NormP p) {
+    constexpr int V = VecOf<T>::V;
+    extern __shared__ float sm[];                        // [RB][C] x (2 or 4)
+    const int C = p.channels, CV = C / V;
+    const RowMap m = row_map(p, CV);
+    const int b = blockIdx.y;
+    const T *x = reinterpret_cast<const T *>(p.x) + (int64_t)b * p.spatial * C;
+    const T *x2 = kTwo ? reinterpret_cast<const T *>(p.x2) + (int64_t)b * p.spatial * C : nullptr;
+    float s1[V], q1[V], s2[V], q2[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { s1[v] = q1[v] = s2[v] = q2[v] = 0.f; }
+    // centre on the first row of the CTA's range to keep the sums small (shift invariance of the variance)
+    float c1[V], c2[V];
+    if (m.row_lo < m.row_hi) {
+        loadv<T, V>(x + m.row_lo * C + m.cv * V, c1);
+        if (kTwo) loadv<T, V>(x2 + m.row_lo * C + m.cv * V, c2);
+    }
+    if (m.active) {
+        for (int64_t row = m.row_lo + m.r; row < m.row_hi; row += m.RB) {
+            float a[V];
+            loadv<T, V>(x + row * C + m.cv * V, a);
+#pragma unroll
+            for (int v = 0; v < V; ++v) { const float d = a[v] - c1[v]; s1[v] += d; q1[v] = fmaf(d, d, q1[v]); }
+            if (kTwo) {
+                loadv<T, V>(x2 + row * C + m.cv * V, a);
+#pragma unroll
+                for (int v = 0; v < V; ++v) { const float d = a[v] - c2[v]; s2[v] += d; q2[v] = fmaf(d, d, q2[v]); }
+            }
+        }
+    }
+    const int RB = m.RB;
+    float *S1 = sm, *Q1 = sm + RB * C, *S2 = sm + 2 * RB * C, *Q2 = sm + 3 * RB * C;
+    if (m.active) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            S1[m.r * C + m.cv * V + v] = s1[v];
+            Q1[m.r * C + m.cv * V + v] = q1[v];
+            if (kTwo) { S2[m.r * C + m.cv * V + v] = s2[v]; Q2[m.r * C + m.cv * V + v] = q2[v]; }
+        }
+    }
+    __syncthreads();
+    const float n = (float)(m.row_hi - m.row_lo);
+    for (int c = threadIdx.x; c < C; c += kNormThreads) {
+        float a = 0.f, q = 0.f, a2 = 0.f, qq2 = 0.f;
+        for (int r = 0; r < RB; ++r) {
+            a += S1[r * C + c]; q += Q1[r * C + c];
+            if (kTwo) { a2 += S2[r * C + c]; qq2 += Q2[r * C + c]; }
+        }
+        // shift back: mean = centre + a/n ; M2 = q - a^2/n
+        const float ctr = n > 0.f ? to_f32<T>(x[m.row_lo * C + c]) : 0.f;
+        float *o = p.partial + (((int64_t)b * gridDim.x + blockIdx.x) * 3) * C + c;
+        o[0] = n;
+        o[C] = n > 0.f ? ctr + a / n : 0.f;
+        o[2 * C] = n > 0.f ? q - a * a / n : 0.f;
+        if (kTwo) {
+            const float ctr2 = n > 0.f ? to_f32<T>(x2[m.row_lo * C + c]) : 0.f;
+            float *o2 = o + (int64_t)p.batch * gridDim.x * 3 * C;
+            o2[0] = n;
+            o2[C] = n > 0.f ? ctr2 + a2 / n : 0.f;
+            o2[2 * C] = n > 0.f ? qq2 - a2 * a2 / n : 0.f;
+        }
+    }
+}
+
+// merge the per-CTA (n, mean, M2) with Chan's parallel formula -> (mean, rstd); one thread per (which, b, c)
+__global__ void in_finalize_fwd_kernel(const float *__restrict__ partial, float *__restrict__ stats, float *__restrict__ stats2,
+                                       int batch, int C, int n_cta, float eps, int two) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = batch * C * (two ? 2 : 1);
+    if (idx >= total) return;
+    const int which = idx / (batch * C);
+    const int b = (idx / C) % batch, c = idx % C;
+    const float *pp = partial + (int64_t)which * batch * n_cta * 3 * C + ((int64_t)b * n_cta * 3) * C + c;
+    double n = 0.0, mean = 0.0, M2 = 0.0;
+    for (int k = 0; k < n_cta; ++k) {
+        const double nk = pp[(int64_t)k * 3 * C], mk = pp[(int64_t)k * 3 * C + C], qk = pp[(int64_t)k * 3 * C + 2 * C];
+        if (nk <= 0.0) continue;
+        const double nt = n + nk, dlt = mk - mean;
+        mean += dlt * nk / nt;
+        M2 += qk + dlt * dlt * n * nk / nt;
+        n = nt;
+    }
+    const double var = n > 0.0 ? M2 / n : 0.0;           // biased, as InstanceNorm uses
+    float *o = (which ? stats2 : stats) + ((int64_t)b * C + c) * 2;
+    o[0] = (float)mean;
+    o[1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward apply: y = act( (x - mean) rstd  [+ (x2 - mean2) rstd2 | + x2] )
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) in_apply_fwd_kernel(const NormP p) {
+    constexpr int V = VecOf<T>::V;
+    const int C = p.channels, CV = C / V;
+    const RowMap m = row_map(p, CV);
+    if (!m.active) return;
+    const int b = blockIdx.y;
+    const int64_t base = (int64_t)b * p.spatial * C;
+    const T *x = reinterpret_cast<const T *>(p.x) + base;
+    const T *x2 = p.mode2 ? reinterpret_cast<const T *>(p.x2) + base : nullptr;
+    T *y = reinterpret_cast<T *>(p.y) + base;
+    float mu[V], rs[V], mu2[V], rs2[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int c = m.cv * V + v;
+        mu[v] = p.stats[((int64_t)b * C + c) * 2];
+        rs[v] = p.stats[((int64_t)b * C + c) * 2 + 1];
+        mu2[v] = 0.f; rs2[v] = 1.f;
+        if (p.mode2 == 2) {
+            mu2[v] = p.stats2[((int64_t)b * C + c) * 2];
+            rs2[v] = p.stats2[((int64_t)b * C + c) * 2 + 1];
+        }
+    }
+    for (int64_t row = m.row_lo + m.r; row < m.row_hi; row += m.RB) {
+        float a[V], o[V];
+        loadv<T, V>(x + row * C + m.cv * V, a);
+#pragma unroll
+        for (int v = 0; v < V; ++v) o[v] = (a[v] - mu[v]) * rs[v];
+        if (p.mode2) {
+            loadv<T, V>(x2 + row * C + m.cv * V, a);
+#pragma unroll
+            for (int v = 0; v < V; ++v) o[v] += (a[v] - mu2[v]) * rs2[v];
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) o[v] = act_fwd(o[v], p.act, p.slope);
+        storev<T, V>(y + row * C + m.cv * V, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward sums: per-CTA  sum g, sum g*xhat1 (, sum g*xhat2)  with g = dy * act'(pre-activation)
+// partial layout: [batch][cta][3][C]
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) in_stats_bwd_kernel(const NormP p) {
+    constexpr int V = VecOf<T>::V;
+    extern __shared__ float sm[];
+    const int C = p.channels, CV = C / V;
+    const RowMap m = row_map(p, CV);
+    const int b = blockIdx.y;
+    const int64_t base = (int64_t)b * p.spatial * C;
+    const T *x = reinterpret_cast<const T *>(p.x) + base;
+    const T *x2 = p.mode2 ? reinterpret_cast<const T *>(p.x2) + base : nullptr;
+    const T *dy = reinterpret_cast<const T *>(p.dy) + base;
+    float mu[V], rs[V], mu2[V], rs2[V], sg[V], sgx[V], sgx2[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int c = m.cv * V + v;
+        mu[v] = p.stats[((int64_t)b * C + c) * 2];
+        rs[v] = p.stats[((int64_t)b * C + c) * 2 + 1];
+        mu2[v] = 0.f; rs2[v] = 1.f;
+        if (p.mode2 == 2) {
+            mu2[v] = p.stats2[((int64_t)b * C + c) * 2];
+            rs2[v] = p.stats2[((int64_t)b * C + c) * 2 + 1];
+        }
+        sg[v] = sgx[v] = sgx2[v] = 0.f;
+    }
+    if (m.active) {
+        for (int64_t row = m.row_lo + m.r; row < m.row_hi; row += m.RB) {
+            float a[V], a2[V], g[V];
+            loadv<T, V>(x + row * C + m.cv * V, a);
+            loadv<T, V>(dy + row * C + m.cv * V, g);
+            if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, a2);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float xh = (a[v] - mu[v]) * rs[v];
+                float pre = xh, xh2 = 0.f;
+                if (p.mode2) { xh2 = (a2[v] - mu2[v]) * rs2[v]; pre += xh2; }
+                const float gg = g[v] * act_grad(pre, p.act, p.slope);
+                sg[v] += gg;
+                sgx[v] = fmaf(gg, xh, sgx[v]);
+                if (p.mode2 == 2) sgx2[v] = fmaf(gg, xh2, sgx2[v]);
+            }
+        }
+    }
+    const int RB = m.RB;
+    float *A = sm, *Bq = sm + RB * C, *Cq = sm + 2 * RB * C;
+    if (m.active) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            A[m.r * C + m.cv * V + v] = sg[v];
+            Bq[m.r * C + m.cv * V + v] = sgx[v];
+            Cq[m.r * C + m.cv * V + v] = sgx2[v];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kNormThreads) {
+        float a = 0.f, q = 0.f, q2 = 0.f;
+        for (int r = 0; r < RB; ++r) { a += A[r * C + c]; q += Bq[r * C + c]; q2 += Cq[r * C + c]; }
+        float *o = p.partial + (((int64_t)b * gridDim.x + blockIdx.x) * 3) * C + c;
+        o[0] = a; o[C] = q; o[2 * C] = q2;
+    }
+}
+
+// sums[b][c] = (mean g, mean g*xhat1, mean g*xhat2)
+__global__ void in_finalize_bwd_kernel(const float *__restrict__ partial, float *__restrict__ sums, int batch, int C, int n_cta,
+                                       double inv_n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * C) return;
+    const int b = idx / C, c = idx % C;
+    const float *pp = partial + ((int64_t)b * n_cta * 3) * C + c;
+    double a = 0.0, q = 0.0, q2 = 0.0;
+    for (int k = 0; k < n_cta; ++k) {
+        a += pp[(int64_t)k * 3 * C]; q += pp[(int64_t)k * 3 * C + C]; q2 += pp[(int64_t)k * 3 * C + 2 * C];
+    }
+    float *o = sums + ((int64_t)b * C + c) * 3;
+    o[0] = (float)(a * inv_n); o[1] = (float)(q * inv_n); o[2] = (float)(q2 * inv_n);
+}
+
+// backward apply: dx = rstd (g - mean g - xhat mean(g xhat)) ;  dx2 likewise (mode 2) or dx2 = g (mode 1)
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) in_apply_bwd_kernel(const NormP p) {
+    constexpr int V = VecOf<T>::V;
+    const int C = p.channels, CV = C / V;
+    const RowMap m = row_map(p, CV);
+    if (!m.active) return;
+    const int b = blockIdx.y;
+    const int64_t base = (int64_t)b * p.spatial * C;
+    const T *x = reinterpret_cast<const T *>(p.x) + base;
+    const T *x2 = p.mode2 ? reinterpret_cast<const T *>(p.x2) + base : nullptr;
+    const T *dy = reinterpret_cast<const T *>(p.dy) + base;
+    T *dx = reinterpret_cast<T *>(p.dx) + base;
+    T *dx2 = (p.mode2 && p.dx2) ? reinterpret_cast<T *>(p.dx2) + base : nullptr;
+    float mu[V], rs[V], mu2[V], rs2[V], mg[V], mgx[V], mgx2[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int c = m.cv * V + v;
+        mu[v] = p.stats[((int64_t)b * C + c) * 2];
+        rs[v] = p.stats[((int64_t)b * C + c) * 2 + 1];
+        mu2[v] = 0.f; rs2[v] = 1.f;
+        if (p.mode2 == 2) {
+            mu2[v] = p.stats2[((int64_t)b * C + c) * 2];
+            rs2[v] = p.stats2[((int64_t)b * C + c) * 2 + 1];
+        }
+        mg[v] = p.sums[((int64_t)b * C + c) * 3];
+        mgx[v] = p.sums[((int64_t)b * C + c) * 3 + 1];
+        mgx2[v] = p.sums[((int64_t)b * C + c) * 3 + 2];
+    }
+    for (int64_t row = m.row_lo + m.r; row < m.row_hi; row += m.RB) {
+        float a[V], a2[V], g[V], o[V], o2[V];
+        loadv<T, V>(x + row * C + m.cv * V, a);
+        loadv<T, V>(dy + row * C + m.cv * V, g);
+        if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, a2);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const float xh = (a[v] - mu[v]) * rs[v];
+            float pre = xh, xh2 = 0.f;
+            if (p.mode2) { xh2 = (a2[v] - mu2[v]) * rs2[v]; pre += xh2; }
+            const float gg = g[v] * act_grad(pre, p.act, p.slope);
+            o[v] = rs[v] * (gg - mg[v] - xh * mgx[v]);
+            o2[v] = p.mode2 == 2 ? rs2[v] * (gg - mg[v] - xh2 * mgx2[v]) : gg;
+        }
+        storev<T, V>(dx + row * C + m.cv * V, o);
+        if (dx2) storev<T, V>(dx2 + row * C + m.cv * V, o2);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t norm_fwd_t(NormP p, cudaStream_t st) {
+    constexpr int V = VecOf<T>::V;
+    const int CV = p.channels / V, RB = kNormThreads / CV;
+    dim3 grid(p.n_cta, p.batch);
+    const bool two = p.mode2 == 2;
+    const size_t smem = (size_t)RB * p.channels * (two ? 4 : 2) * sizeof(float);
+    if (two) in_stats_fwd_kernel<T, true><<<grid, kNormThreads, smem, st>>>(p);
+    else in_stats_fwd_kernel<T, false><<<grid, kNormThreads, smem, st>>>(p);
+    count_launch();
+    const int tot = p.batch * p.channels * (two ? 2 : 1);
+    in_finalize_fwd_kernel<<<(tot + 127) / 128, 128, 0, st>>>(p.partial, p.stats, p.stats2, p.batch, p.channels, p.n_cta, p.eps, two ? 1 : 0);
+    count_launch();
+    in_apply_fwd_kernel<T><<<grid, kNormThreads, 0, st>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t norm_bwd_t(NormP p, cudaStream_t st) {
+    constexpr int V = VecOf<T>::V;
+    const int CV = p.channels / V, RB = kNormThreads / CV;
+    dim3 grid(p.n_cta, p.batch);
+    const size_t smem = (size_t)RB * p.channels * 3 * sizeof(float);
+    in_stats_bwd_kernel<T><<<grid, kNormThreads, smem, st>>>(p);
+    count_launch();
+    const int tot = p.batch * p.channels;
+    in_finalize_bwd_kernel<<<(tot + 127) / 128, 128, 0, st>>>(p.partial, p.sums, p.batch, p.channels, p.n_cta, 1.0 / (double)p.spatial);
+    count_launch();
+    in_apply_bwd_kernel<T><<<grid, kNormThreads, 0, st>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t instnorm_dispatch(const NormP &p, int dtype, bool bwd, cudaStream_t st) {
+    switch (dtype) {
+        case 0: return bwd ? norm_bwd_t<float>(p, st) : norm_fwd_t<float>(p, st);
+        case 1: return bwd ? norm_bwd_t<__half>(p, st) : norm_fwd_t<__half>(p, st);
+        default: return bwd ? norm_bwd_t<__nv_bfloat16>(p, st) : norm_fwd_t<__nv_bfloat16>(p, st);
+    }
+}
+
+}  // namespace smb

@@ -8,7 +8,11 @@ Module / attribute names reproduce the reference's 291 state_dict keys (SURVEY.m
 The MONAI blocks are restated minimally (monai/networks/blocks/dynunet_block.py:25-111,247-267,
 unetr_block.py:22-86,209-259, convolutions.py:25): dense Conv3d / ConvTranspose3d(k2,s2) without bias,
 InstanceNorm3d(affine=False, eps=1e-5), LeakyReLU(0.01).  The dense 3-D convolutions are library (cuDNN) calls,
-as in the reference; the TSMamba token mixer is the native path.
+as in the reference; the TSMamba token mixer and every InstanceNorm(+activation+residual) chain are native kernels.
+
+Data layout: activations are kept channels-last (NDHWC) end to end, so (i) cuDNN's tensor-core convolutions need
+no NCHW<->NHWC conversion kernels, (ii) the (B, L, C) token view that MambaLayer needs is free (the reference pays a
+transpose copy each way, segmamba.py:69,74), and (iii) the fused instance-norm kernels stream full rows.
 """
 from __future__ import annotations
 
@@ -16,7 +20,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .instance_norm import fused_instance_norm
 from .mamba_simple import Mamba
+
+_CL = torch.channels_last_3d
 
 
 class _Conv(nn.Sequential):
@@ -48,13 +55,12 @@ class UnetResBlock(nn.Module):
             self.norm3 = nn.InstanceNorm3d(out_channels)
 
     def forward(self, inp):
-        residual = inp
-        out = self.lrelu(self.norm1(self.conv1(inp)))
-        out = self.norm2(self.conv2(out))
-        if self.downsample:
-            residual = self.norm3(self.conv3(residual))
-        out = out + residual
-        return self.lrelu(out)
+        # norm1/norm2/norm3/lrelu stay registered for structural parity; the math runs in the fused kernels
+        out = fused_instance_norm(self.conv1(inp), "leaky_relu", 0.01)                    # dynunet_block.py:100-102
+        out = self.conv2(out)
+        if self.downsample:                                                               # :105-110
+            return fused_instance_norm(out, "leaky_relu", 0.01, add=self.conv3(inp), add_norm=True)
+        return fused_instance_norm(out, "leaky_relu", 0.01, add=inp)
 
 
 class UnetrBasicBlock(nn.Module):
@@ -110,6 +116,12 @@ class MambaLayer(nn.Module):
         assert C == self.dim
         img_dims = x.shape[2:]
         n_tokens = img_dims.numel()
+        if x.is_contiguous(memory_format=_CL):
+            # channels-last storage IS the (B, L, C) token matrix: both reshapes are views
+            x_flat = x.permute(0, 2, 3, 4, 1).reshape(B, n_tokens, C)
+            x_mamba = self.mamba(self.norm(x_flat))
+            out = x_mamba.reshape(B, *img_dims, C).permute(0, 4, 1, 2, 3)
+            return out + x
         x_flat = x.reshape(B, C, n_tokens).transpose(-1, -2)
         x_norm = self.norm(x_flat)
         x_mamba = self.mamba(x_norm)
@@ -150,10 +162,10 @@ class GSC(nn.Module):
 
     def forward(self, x):
         x_residual = x
-        x1 = self.nonliner(self.norm(self.proj(x)))
-        x1 = self.nonliner2(self.norm2(self.proj2(x1)))
-        x2 = self.nonliner3(self.norm3(self.proj3(x)))
-        x = self.nonliner4(self.norm4(self.proj4(x1 + x2)))
+        x1 = fused_instance_norm(self.proj(x), "relu")
+        x1 = fused_instance_norm(self.proj2(x1), "relu")
+        x2 = fused_instance_norm(self.proj3(x), "relu")
+        x = fused_instance_norm(self.proj4(x1 + x2), "relu")
         return x + x_residual
 
 
@@ -183,12 +195,14 @@ class MambaEncoder(nn.Module):
     def forward_features(self, x):
         outs = []
         for i in range(4):
-            x = self.downsample_layers[i](x)
+            if i == 0:
+                x = self.downsample_layers[0](x)
+            else:                                       # Sequential(InstanceNorm3d, Conv3d), segmamba.py:145-149
+                x = self.downsample_layers[i][1](fused_instance_norm(x))
             x = self.gscs[i](x)
             x = self.stages[i](x)
             if i in self.out_indices:
-                x_out = getattr(self, f"norm{i}")(x)
-                outs.append(self.mlps[i](x_out))
+                outs.append(self.mlps[i](fused_instance_norm(x)))          # norm{i} then MlpChannel, :183-187
         return tuple(outs)
 
     def forward(self, x):
@@ -225,8 +239,11 @@ class SegMamba(nn.Module):
         self.decoder1 = UnetrBasicBlock(in_channels=feat_size[0], out_channels=feat_size[0], kernel_size=3, stride=1, **kw)
         # the reference hard-codes in_channels=48 here (segmamba.py:319)
         self.out = UnetOutBlock(spatial_dims=spatial_dims, in_channels=48, out_channels=out_chans)
+        # conv weights in channels-last storage (values / state_dict unchanged)
+        self.to(memory_format=_CL)
 
     def forward(self, x_in):
+        x_in = x_in.contiguous(memory_format=_CL)
         outs = self.vit(x_in)
         enc1 = self.encoder1(x_in)
         enc2 = self.encoder2(outs[0])
@@ -238,4 +255,4 @@ class SegMamba(nn.Module):
         dec1 = self.decoder3(dec2, enc2)
         dec0 = self.decoder2(dec1, enc1)
         out = self.decoder1(dec0)
-        return self.out(out)
+        return self.out(out).contiguous()

@@ -49,7 +49,8 @@ def test_library_exports_match_header():
 
 @pytest.mark.parametrize("cname,pyname", [("smb_scan_fwd_args", "ScanFwdArgs"), ("smb_scan_bwd_args", "ScanBwdArgs"),
                                           ("smb_conv1d_args", "Conv1dArgs"), ("smb_conv1d_bwd_args", "Conv1dBwdArgs"),
-                                          ("smb_seq_permute_args", "SeqPermuteArgs")])
+                                          ("smb_seq_permute_args", "SeqPermuteArgs"), ("smb_instnorm_args", "InstNormArgs"),
+                                          ("smb_instnorm_bwd_args", "InstNormBwdArgs")])
 def test_ctypes_structs_match_header(cname, pyname):
     from segmamba_b200 import _lib
     py = [f[0] for f in getattr(_lib, pyname)._fields_]
