@@ -38,8 +38,12 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// softplus with the reference's threshold (selective_scan_fwd_kernel.cuh:155)
-__device__ __forceinline__ float softplus20(float x) { return x <= 20.f ? log1pf(__expf(x)) : x; }
+// softplus with the reference's threshold (selective_scan_fwd_kernel.cuh:155); select, not branch, so that a run of
+// positions can be processed as straight-line code
+__device__ __forceinline__ float softplus20(float x) {
+    const float sp = log1pf(__expf(fminf(x, 20.f)));
+    return x <= 20.f ? sp : x;
+}
 __device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------
@@ -189,6 +193,42 @@ __device__ __forceinline__ void store_tile(const float *tile, T *base, int64_t r
                 }
             }
         }
+    }
+}
+
+// In-place pre-passes over the lane's own row of a tile (lane == row == channel), vectorised and branch-free so the
+// serial recurrence loop that follows contains no transcendental chains:
+//   dt   <- softplus?(delta + bias), forced to 0 for positions >= nvalid (a = 1, b = 0: the scan identity)
+//   gate <- z * sigmoid(z)
+__device__ __forceinline__ void prepass_dt(float *tile, int lane, float bias, bool softplus, int nvalid) {
+#pragma unroll
+    for (int c = 0; c < kTile / 4; ++c) {
+        float4 v = tile_read4(tile, lane, c);
+        float x[4] = {v.x + bias, v.y + bias, v.z + bias, v.w + bias};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (softplus) x[e] = softplus20(x[e]);
+            if (4 * c + e >= nvalid) x[e] = 0.f;
+        }
+        tile_write4(tile, lane, c, make_float4(x[0], x[1], x[2], x[3]));
+    }
+}
+__device__ __forceinline__ void prepass_silu(float *tile, int lane) {
+#pragma unroll
+    for (int c = 0; c < kTile / 4; ++c) {
+        float4 v = tile_read4(tile, lane, c);
+        v.x *= sigmoidf(v.x); v.y *= sigmoidf(v.y); v.z *= sigmoidf(v.z); v.w *= sigmoidf(v.w);
+        tile_write4(tile, lane, c, v);
+    }
+}
+// g <- g * silu(z)   (both tiles are this lane's rows)
+__device__ __forceinline__ void prepass_gate_grad(float *gtile, const float *ztile, int lane) {
+#pragma unroll
+    for (int c = 0; c < kTile / 4; ++c) {
+        float4 g = tile_read4(gtile, lane, c);
+        const float4 z = tile_read4(ztile, lane, c);
+        g.x *= z.x * sigmoidf(z.x); g.y *= z.y * sigmoidf(z.y); g.z *= z.z * sigmoidf(z.z); g.w *= z.w * sigmoidf(z.w);
+        tile_write4(gtile, lane, c, g);
     }
 }
 

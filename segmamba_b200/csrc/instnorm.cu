@@ -154,28 +154,43 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_fwd_kernel(const NormP 
     }
 }
 
-// merge the per-CTA (n, mean, M2) with Chan's parallel formula -> (mean, rstd); one thread per (which, b, c)
-__global__ void in_finalize_fwd_kernel(const float *__restrict__ partial, float *__restrict__ stats, float *__restrict__ stats2,
-                                       int batch, int C, int n_cta, float eps, int two) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = batch * C * (two ? 2 : 1);
-    if (idx >= total) return;
-    const int which = idx / (batch * C);
-    const int b = (idx / C) % batch, c = idx % C;
-    const float *pp = partial + (int64_t)which * batch * n_cta * 3 * C + ((int64_t)b * n_cta * 3) * C + c;
-    double n = 0.0, mean = 0.0, M2 = 0.0;
-    for (int k = 0; k < n_cta; ++k) {
-        const double nk = pp[(int64_t)k * 3 * C], mk = pp[(int64_t)k * 3 * C + C], qk = pp[(int64_t)k * 3 * C + 2 * C];
-        if (nk <= 0.0) continue;
-        const double nt = n + nk, dlt = mk - mean;
-        mean += dlt * nk / nt;
-        M2 += qk + dlt * dlt * n * nk / nt;
-        n = nt;
+// merge the per-CTA (n, mean, M2) with Chan's parallel formula -> (mean, rstd).
+// Block = 32 channels x 8 partial-groups (coalesced 128-byte reads along the channel axis); grid = (C/32, batch, which).
+__global__ void __launch_bounds__(256) in_finalize_fwd_kernel(const float *__restrict__ partial, float *__restrict__ stats,
+                                                              float *__restrict__ stats2, int batch, int C, int n_cta, float eps) {
+    __shared__ float sn[8][32], smean[8][32], sm2[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx, b = blockIdx.y, which = blockIdx.z;
+    float n = 0.f, mean = 0.f, M2 = 0.f;
+    if (c < C) {
+        const float *pp = partial + (int64_t)which * batch * n_cta * 3 * C + ((int64_t)b * n_cta * 3) * C + c;
+        for (int k = ty; k < n_cta; k += 8) {
+            const float nk = pp[(int64_t)k * 3 * C], mk = pp[(int64_t)k * 3 * C + C], qk = pp[(int64_t)k * 3 * C + 2 * C];
+            if (nk > 0.f) {
+                const float nt = n + nk, dlt = mk - mean;
+                mean += dlt * (nk / nt);
+                M2 += qk + dlt * dlt * (n * nk / nt);
+                n = nt;
+            }
+        }
     }
-    const double var = n > 0.0 ? M2 / n : 0.0;           // biased, as InstanceNorm uses
-    float *o = (which ? stats2 : stats) + ((int64_t)b * C + c) * 2;
-    o[0] = (float)mean;
-    o[1] = (float)(1.0 / sqrt(var + (double)eps));
+    sn[ty][tx] = n; smean[ty][tx] = mean; sm2[ty][tx] = M2;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        double dn = 0.0, dmean = 0.0, dM2 = 0.0;
+        for (int g = 0; g < 8; ++g) {
+            const double nk = sn[g][tx], mk = smean[g][tx], qk = sm2[g][tx];
+            if (nk <= 0.0) continue;
+            const double nt = dn + nk, dlt = mk - dmean;
+            dmean += dlt * nk / nt;
+            dM2 += qk + dlt * dlt * dn * nk / nt;
+            dn = nt;
+        }
+        const double var = dn > 0.0 ? dM2 / dn : 0.0;    // biased, as InstanceNorm uses
+        float *o = (which ? stats2 : stats) + ((int64_t)b * C + c) * 2;
+        o[0] = (float)dmean;
+        o[1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -285,19 +300,27 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_bwd_kernel(const NormP 
     }
 }
 
-// sums[b][c] = (mean g, mean g*xhat1, mean g*xhat2)
-__global__ void in_finalize_bwd_kernel(const float *__restrict__ partial, float *__restrict__ sums, int batch, int C, int n_cta,
-                                       double inv_n) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= batch * C) return;
-    const int b = idx / C, c = idx % C;
-    const float *pp = partial + ((int64_t)b * n_cta * 3) * C + c;
-    double a = 0.0, q = 0.0, q2 = 0.0;
-    for (int k = 0; k < n_cta; ++k) {
-        a += pp[(int64_t)k * 3 * C]; q += pp[(int64_t)k * 3 * C + C]; q2 += pp[(int64_t)k * 3 * C + 2 * C];
+// sums[b][c] = (mean g, mean g*xhat1, mean g*xhat2); same 32 x 8 mapping as the forward finalize
+__global__ void __launch_bounds__(256) in_finalize_bwd_kernel(const float *__restrict__ partial, float *__restrict__ sums, int batch,
+                                                              int C, int n_cta, float inv_n) {
+    __shared__ float sa[8][32], sq[8][32], sq2[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx, b = blockIdx.y;
+    float a = 0.f, q = 0.f, q2 = 0.f;
+    if (c < C) {
+        const float *pp = partial + ((int64_t)b * n_cta * 3) * C + c;
+        for (int k = ty; k < n_cta; k += 8) {
+            a += pp[(int64_t)k * 3 * C]; q += pp[(int64_t)k * 3 * C + C]; q2 += pp[(int64_t)k * 3 * C + 2 * C];
+        }
     }
-    float *o = sums + ((int64_t)b * C + c) * 3;
-    o[0] = (float)(a * inv_n); o[1] = (float)(q * inv_n); o[2] = (float)(q2 * inv_n);
+    sa[ty][tx] = a; sq[ty][tx] = q; sq2[ty][tx] = q2;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        double da = 0.0, dq = 0.0, dq2 = 0.0;
+        for (int g = 0; g < 8; ++g) { da += sa[g][tx]; dq += sq[g][tx]; dq2 += sq2[g][tx]; }
+        float *o = sums + ((int64_t)b * C + c) * 3;
+        o[0] = (float)(da * inv_n); o[1] = (float)(dq * inv_n); o[2] = (float)(dq2 * inv_n);
+    }
 }
 
 // backward apply: dx = rstd (g - mean g - xhat mean(g xhat)) ;  dx2 likewise (mode 2) or dx2 = g (mode 1)
@@ -361,8 +384,8 @@ static cudaError_t norm_fwd_t(NormP p, cudaStream_t st) {
     if (two) in_stats_fwd_kernel<T, true><<<grid, kNormThreads, smem, st>>>(p);
     else in_stats_fwd_kernel<T, false><<<grid, kNormThreads, smem, st>>>(p);
     count_launch();
-    const int tot = p.batch * p.channels * (two ? 2 : 1);
-    in_finalize_fwd_kernel<<<(tot + 127) / 128, 128, 0, st>>>(p.partial, p.stats, p.stats2, p.batch, p.channels, p.n_cta, p.eps, two ? 1 : 0);
+    dim3 fg((p.channels + 31) / 32, p.batch, two ? 2 : 1);
+    in_finalize_fwd_kernel<<<fg, 256, 0, st>>>(p.partial, p.stats, p.stats2, p.batch, p.channels, p.n_cta, p.eps);
     count_launch();
     in_apply_fwd_kernel<T><<<grid, kNormThreads, 0, st>>>(p);
     count_launch();
@@ -377,8 +400,8 @@ static cudaError_t norm_bwd_t(NormP p, cudaStream_t st) {
     const size_t smem = (size_t)RB * p.channels * 3 * sizeof(float);
     in_stats_bwd_kernel<T><<<grid, kNormThreads, smem, st>>>(p);
     count_launch();
-    const int tot = p.batch * p.channels;
-    in_finalize_bwd_kernel<<<(tot + 127) / 128, 128, 0, st>>>(p.partial, p.sums, p.batch, p.channels, p.n_cta, 1.0 / (double)p.spatial);
+    dim3 fg((p.channels + 31) / 32, p.batch);
+    in_finalize_bwd_kernel<<<fg, 256, 0, st>>>(p.partial, p.sums, p.batch, p.channels, p.n_cta, (float)(1.0 / (double)p.spatial));
     count_launch();
     in_apply_bwd_kernel<T><<<grid, kNormThreads, 0, st>>>(p);
     count_launch();

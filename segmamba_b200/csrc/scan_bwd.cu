@@ -67,34 +67,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
         if (kHasZ) fill_tile<T>(s_z, z, p.z_ds, wi.nrows, j0, p.L, p.reverse, lane);
         fill_bc_tile<T, N>(s_C, Cm, p.C_ns, p.C_ls, j0, p.L, p.reverse, lane);
         __syncwarp();
-        const int qmax = min(kTile, j_end - j0);
-        for (int c = (qmax - 1) >> 2; c >= 0; --c) {
+        prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions: a = 1, and g == 0 there
+        if (kHasZ) prepass_gate_grad(s_g, s_z, lane);
+#pragma unroll 2
+        for (int c = kTile / 4 - 1; c >= 0; --c) {
             const float4 d4 = tile_read4(s_dt, lane, c);
             const float4 g4 = tile_read4(s_g, lane, c);
-            float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kHasZ) z4 = tile_read4(s_z, lane, c);
             const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
             const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
             for (int e = 3; e >= 0; --e) {
                 const int q = 4 * c + e;
-                if (q < qmax) {
-                    float dt = dd[e] + bias;
-                    if (p.softplus) dt = softplus20(dt);
-                    float g = gg[e];
-                    if (kHasZ) g *= zz[e] * sigmoidf(zz[e]);
-                    sumdt += dt;
+                const float dt = dd[e];
+                const float g = gg[e];
+                sumdt += dt;
 #pragma unroll
-                    for (int jn = 0; jn < N / 4; ++jn) {
-                        const float4 c4 = bc_read4<N>(s_C, q, jn);
-                        const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                for (int jn = 0; jn < N / 4; ++jn) {
+                    const float4 c4 = bc_read4<N>(s_C, q, jn);
+                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int n = 4 * jn + k;
-                            const float a = ex2(dt * A2[n]);
-                            mu[n] = a * fmaf(g, cc[k], mu[n]);
-                        }
+                    for (int k = 0; k < 4; ++k) {
+                        const int n = 4 * jn + k;
+                        const float a = ex2(dt * A2[n]);
+                        mu[n] = a * fmaf(g, cc[k], mu[n]);
                     }
                 }
             }

@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_agg_kernel(const S
         fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
         fill_bc_tile<T, N>(s_B, Bm, p.B_ns, p.B_ls, j0, p.L, p.reverse, lane);
         __syncwarp();
-        const int qmax = min(kTile, j_end - j0);
-        for (int c = 0; c * 4 < qmax; ++c) {
+        prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions become scan identities
+#pragma unroll 2
+        for (int c = 0; c < kTile / 4; ++c) {
             const float4 u4 = tile_read4(s_u, lane, c);
             const float4 d4 = tile_read4(s_dt, lane, c);
             const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
@@ -62,21 +63,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_agg_kernel(const S
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int q = 4 * c + e;
-                if (q < qmax) {
-                    float dt = dd[e] + bias;
-                    if (p.softplus) dt = softplus20(dt);
-                    const float du = dt * uu[e];
-                    sumdt += dt;
+                const float dt = dd[e];
+                const float du = dt * uu[e];
+                sumdt += dt;
 #pragma unroll
-                    for (int jn = 0; jn < N / 4; ++jn) {
-                        const float4 b4 = bc_read4<N>(s_B, q, jn);
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                for (int jn = 0; jn < N / 4; ++jn) {
+                    const float4 b4 = bc_read4<N>(s_B, q, jn);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int n = 4 * jn + k;
-                            const float a = ex2(dt * A2[n]);
-                            h[n] = fmaf(a, h[n], du * bb[k]);
-                        }
+                    for (int k = 0; k < 4; ++k) {
+                        const int n = 4 * jn + k;
+                        const float a = ex2(dt * A2[n]);
+                        h[n] = fmaf(a, h[n], du * bb[k]);
                     }
                 }
             }
@@ -169,7 +167,7 @@ __global__ void __launch_bounds__(1024) carry_kernel(const float *__restrict__ P
 // pass 3
 // ---------------------------------------------------------------------------------------------
 template <typename T, int N, bool kHasZ>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_main_kernel(const ScanP p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(const ScanP p) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * kWarpsPerCta + warp;
@@ -218,8 +216,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_main_kernel(const 
         fill_bc_tile<T, N>(s_B, Bm, p.B_ns, p.B_ls, j0, p.L, p.reverse, lane);
         fill_bc_tile<T, N>(s_C, Cm, p.C_ns, p.C_ls, j0, p.L, p.reverse, lane);
         __syncwarp();
-        const int qmax = min(kTile, j_end - j0);
-        for (int c = 0; c * 4 < qmax; ++c) {
+        prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions become scan identities
+        if (kHasZ) prepass_silu(s_z, lane);
+#pragma unroll 2
+        for (int c = 0; c < kTile / 4; ++c) {
             const float4 u4 = tile_read4(s_u, lane, c);
             const float4 d4 = tile_read4(s_dt, lane, c);
             float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -227,34 +227,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_main_kernel(const 
             const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
             const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
             const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-            float yy[4] = {0.f, 0.f, 0.f, 0.f}, yz[4] = {0.f, 0.f, 0.f, 0.f};
+            float yy[4], yz[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int q = 4 * c + e;
-                if (q < qmax) {
-                    float dt = dd[e] + bias;
-                    if (p.softplus) dt = softplus20(dt);
-                    const float du = dt * uu[e];
-                    float y0 = 0.f, y1 = 0.f;
+                const float dt = dd[e];
+                const float du = dt * uu[e];
+                float y0 = 0.f, y1 = 0.f;
 #pragma unroll
-                    for (int jn = 0; jn < N / 4; ++jn) {
-                        const float4 b4 = bc_read4<N>(s_B, q, jn);
-                        const float4 c4 = bc_read4<N>(s_C, q, jn);
-                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                        const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                for (int jn = 0; jn < N / 4; ++jn) {
+                    const float4 b4 = bc_read4<N>(s_B, q, jn);
+                    const float4 c4 = bc_read4<N>(s_C, q, jn);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int n = 4 * jn + k;
-                            const float a = ex2(dt * A2[n]);
-                            h[n] = fmaf(a, h[n], du * bb[k]);
-                            if (k & 1) y1 = fmaf(cc[k], h[n], y1);
-                            else y0 = fmaf(cc[k], h[n], y0);
-                        }
+                    for (int k = 0; k < 4; ++k) {
+                        const int n = 4 * jn + k;
+                        const float a = ex2(dt * A2[n]);
+                        h[n] = fmaf(a, h[n], du * bb[k]);
+                        if (k & 1) y1 = fmaf(cc[k], h[n], y1);
+                        else y0 = fmaf(cc[k], h[n], y0);
                     }
-                    const float y = fmaf(Dv, uu[e], y0 + y1);
-                    yy[e] = y;
-                    if (kHasZ) yz[e] = y * zz[e] * sigmoidf(zz[e]);
                 }
+                const float y = fmaf(Dv, uu[e], y0 + y1);
+                yy[e] = y;
+                yz[e] = y * zz[e];                                  // zz already holds silu(z)
             }
             // in-place: the same lane that consumed (row, c) overwrites it
             tile_write4(s_u, lane, c, make_float4(yy[0], yy[1], yy[2], yy[3]));

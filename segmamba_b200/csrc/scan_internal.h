@@ -47,10 +47,10 @@ __device__ __forceinline__ WorkItem decode_work(const ScanP &p, int w) {
     return wi;
 }
 
-// Segment length heuristic (host): largest S in {256..2048} that still yields >= 8 warps per SM on a
-// 148-SM B200; S divides 2048 so the reference's 2048-position chunk states fall on segment ends.
+// Segment length heuristic (host): largest S in {256..2048} that still yields >= 24 warps per SM (two waves at the
+// 12-warp residency the kernels reach) on a 148-SM B200; S divides 2048 so the reference's 2048-position chunk states fall on segment ends.
 inline int plan_segment(int batch, int n_tiles, int L) {
-    const long target = 148L * 8;
+    const long target = 148L * 24;
     int S = 2048;
     while (S > kCkpt && (long)batch * n_tiles * ((L + S - 1) / S) < target) S >>= 1;
     return S;
