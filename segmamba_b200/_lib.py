@@ -14,7 +14,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsegmamba_b200.so")
+LIB_PATH = os.environ.get("SMB_LIB") or os.path.join(_HERE, "libsegmamba_b200.so")   # SMB_LIB: tuning variants
 CSRC = os.path.join(_HERE, "csrc")
 
 SMB_F32, SMB_F16, SMB_BF16 = 0, 1, 2

@@ -38,6 +38,36 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// ---- packed fp32x2 (Blackwell FFMA2 / FMUL2 / FADD2: two lanes of fp32 per issue slot) ----
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 ex2x2_mufu(float2 x) { return make_float2(ex2(x.x), ex2(x.y)); }
+// 2^x for x <= 0 on the FMA pipe (Cody-Waite split + degree-6 polynomial, rel. error ~2e-7, same class as MUFU.EX2):
+// the scan kernels are MUFU-bound, so a fraction of the decays is evaluated here to balance the two pipes.
+__device__ __forceinline__ float2 ex2x2_poly(float2 x) {
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+    const float2 t = __fadd2_rn(x, f2(12582912.f, 12582912.f));          // round to nearest integer in the low mantissa bits
+    const float2 n = __fadd2_rn(t, f2(-12582912.f, -12582912.f));
+    const float2 f = __ffma2_rn(n, f2(-1.f, -1.f), x);                    // f in [-0.5, 0.5]
+    float2 p = f2(1.535336188319500e-4f, 1.535336188319500e-4f);
+    p = __ffma2_rn(p, f, f2(1.339887440266574e-3f, 1.339887440266574e-3f));
+    p = __ffma2_rn(p, f, f2(9.618437357674640e-3f, 9.618437357674640e-3f));
+    p = __ffma2_rn(p, f, f2(5.550332471162809e-2f, 5.550332471162809e-2f));
+    p = __ffma2_rn(p, f, f2(2.402264791363012e-1f, 2.402264791363012e-1f));
+    p = __ffma2_rn(p, f, f2(6.931472028550421e-1f, 6.931472028550421e-1f));
+    p = __ffma2_rn(p, f, f2(1.f, 1.f));
+    return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                       __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+// which state pairs take the polynomial path (bit m = pair m); tuned on B200, see DESIGN.md section 3.1
+#ifndef SMB_POLY_MASK
+#define SMB_POLY_MASK 0x11
+#endif
+template <int M> __device__ __forceinline__ float2 decay2(float2 arg) {
+    if ((SMB_POLY_MASK >> M) & 1) return ex2x2_poly(arg);
+    return ex2x2_mufu(arg);
+}
+
 // softplus with the reference's threshold (selective_scan_fwd_kernel.cuh:155); select, not branch, so that a run of
 // positions can be processed as straight-line code
 __device__ __forceinline__ float softplus20(float x) {

@@ -108,7 +108,25 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_fwd_kernel(const NormP 
         if (kTwo) loadv<T, V>(x2 + m.row_lo * C + m.cv * V, c2);
     }
     if (m.active) {
-        for (int64_t row = m.row_lo + m.r; row < m.row_hi; row += m.RB) {
+        constexpr int U = 4;                             // rows in flight per thread (memory-level parallelism)
+        int64_t row = m.row_lo + m.r;
+        for (; row + (int64_t)(U - 1) * m.RB < m.row_hi; row += (int64_t)U * m.RB) {
+            float a[U][V], a2[U][V];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                loadv<T, V>(x + (row + (int64_t)k * m.RB) * C + m.cv * V, a[k]);
+                if (kTwo) loadv<T, V>(x2 + (row + (int64_t)k * m.RB) * C + m.cv * V, a2[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float d = a[k][v] - c1[v]; s1[v] += d; q1[v] = fmaf(d, d, q1[v]);
+                    if (kTwo) { const float e = a2[k][v] - c2[v]; s2[v] += e; q2[v] = fmaf(e, e, q2[v]); }
+                }
+            }
+        }
+        for (; row < m.row_hi; row += m.RB) {
             float a[V];
             loadv<T, V>(x + row * C + m.cv * V, a);
 #pragma unroll
@@ -219,19 +237,31 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_fwd_kernel(const NormP 
             rs2[v] = p.stats2[((int64_t)b * C + c) * 2 + 1];
         }
     }
-    for (int64_t row = m.row_lo + m.r; row < m.row_hi; row += m.RB) {
-        float a[V], o[V];
-        loadv<T, V>(x + row * C + m.cv * V, a);
+    constexpr int U = 4;
+    for (int64_t row0 = m.row_lo + m.r; row0 < m.row_hi; row0 += (int64_t)U * m.RB) {
+        float a[U][V], b2[U][V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) o[v] = (a[v] - mu[v]) * rs[v];
-        if (p.mode2) {
-            loadv<T, V>(x2 + row * C + m.cv * V, a);
-#pragma unroll
-            for (int v = 0; v < V; ++v) o[v] += (a[v] - mu2[v]) * rs2[v];
+        for (int k = 0; k < U; ++k) {
+            const int64_t row = row0 + (int64_t)k * m.RB;
+            if (row < m.row_hi) {
+                loadv<T, V>(x + row * C + m.cv * V, a[k]);
+                if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, b2[k]);
+            }
         }
 #pragma unroll
-        for (int v = 0; v < V; ++v) o[v] = act_fwd(o[v], p.act, p.slope);
-        storev<T, V>(y + row * C + m.cv * V, o);
+        for (int k = 0; k < U; ++k) {
+            const int64_t row = row0 + (int64_t)k * m.RB;
+            if (row < m.row_hi) {
+                float o[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    float t = (a[k][v] - mu[v]) * rs[v];
+                    if (p.mode2) t += (b2[k][v] - mu2[v]) * rs2[v];
+                    o[v] = act_fwd(t, p.act, p.slope);
+                }
+                storev<T, V>(y + row * C + m.cv * V, o);
+            }
+        }
     }
 }
 
@@ -264,20 +294,33 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_bwd_kernel(const NormP 
         sg[v] = sgx[v] = sgx2[v] = 0.f;
     }
     if (m.active) {
-        for (int64_t row = m.row_lo + m.r; row < m.row_hi; row += m.RB) {
-            float a[V], a2[V], g[V];
-            loadv<T, V>(x + row * C + m.cv * V, a);
-            loadv<T, V>(dy + row * C + m.cv * V, g);
-            if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, a2);
+        constexpr int U = 2;
+        for (int64_t row0 = m.row_lo + m.r; row0 < m.row_hi; row0 += (int64_t)U * m.RB) {
+            float a[U][V], a2[U][V], g[U][V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const float xh = (a[v] - mu[v]) * rs[v];
-                float pre = xh, xh2 = 0.f;
-                if (p.mode2) { xh2 = (a2[v] - mu2[v]) * rs2[v]; pre += xh2; }
-                const float gg = g[v] * act_grad(pre, p.act, p.slope);
-                sg[v] += gg;
-                sgx[v] = fmaf(gg, xh, sgx[v]);
-                if (p.mode2 == 2) sgx2[v] = fmaf(gg, xh2, sgx2[v]);
+            for (int k = 0; k < U; ++k) {
+                const int64_t row = row0 + (int64_t)k * m.RB;
+                if (row < m.row_hi) {
+                    loadv<T, V>(x + row * C + m.cv * V, a[k]);
+                    loadv<T, V>(dy + row * C + m.cv * V, g[k]);
+                    if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, a2[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int64_t row = row0 + (int64_t)k * m.RB;
+                if (row < m.row_hi) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        const float xh = (a[k][v] - mu[v]) * rs[v];
+                        float pre = xh, xh2 = 0.f;
+                        if (p.mode2) { xh2 = (a2[k][v] - mu2[v]) * rs2[v]; pre += xh2; }
+                        const float gg = g[k][v] * act_grad(pre, p.act, p.slope);
+                        sg[v] += gg;
+                        sgx[v] = fmaf(gg, xh, sgx[v]);
+                        if (p.mode2 == 2) sgx2[v] = fmaf(gg, xh2, sgx2[v]);
+                    }
+                }
             }
         }
     }
@@ -352,22 +395,36 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_bwd_kernel(const NormP 
         mgx[v] = p.sums[((int64_t)b * C + c) * 3 + 1];
         mgx2[v] = p.sums[((int64_t)b * C + c) * 3 + 2];
     }
-    for (int64_t row = m.row_lo + m.r; row < m.row_hi; row += m.RB) {
-        float a[V], a2[V], g[V], o[V], o2[V];
-        loadv<T, V>(x + row * C + m.cv * V, a);
-        loadv<T, V>(dy + row * C + m.cv * V, g);
-        if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, a2);
+    constexpr int U = 2;
+    for (int64_t row0 = m.row_lo + m.r; row0 < m.row_hi; row0 += (int64_t)U * m.RB) {
+        float a[U][V], a2[U][V], g[U][V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            const float xh = (a[v] - mu[v]) * rs[v];
-            float pre = xh, xh2 = 0.f;
-            if (p.mode2) { xh2 = (a2[v] - mu2[v]) * rs2[v]; pre += xh2; }
-            const float gg = g[v] * act_grad(pre, p.act, p.slope);
-            o[v] = rs[v] * (gg - mg[v] - xh * mgx[v]);
-            o2[v] = p.mode2 == 2 ? rs2[v] * (gg - mg[v] - xh2 * mgx2[v]) : gg;
+        for (int k = 0; k < U; ++k) {
+            const int64_t row = row0 + (int64_t)k * m.RB;
+            if (row < m.row_hi) {
+                loadv<T, V>(x + row * C + m.cv * V, a[k]);
+                loadv<T, V>(dy + row * C + m.cv * V, g[k]);
+                if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, a2[k]);
+            }
         }
-        storev<T, V>(dx + row * C + m.cv * V, o);
-        if (dx2) storev<T, V>(dx2 + row * C + m.cv * V, o2);
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t row = row0 + (int64_t)k * m.RB;
+            if (row < m.row_hi) {
+                float o[V], o2[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const float xh = (a[k][v] - mu[v]) * rs[v];
+                    float pre = xh, xh2 = 0.f;
+                    if (p.mode2) { xh2 = (a2[k][v] - mu2[v]) * rs2[v]; pre += xh2; }
+                    const float gg = g[k][v] * act_grad(pre, p.act, p.slope);
+                    o[v] = rs[v] * (gg - mg[v] - xh * mgx[v]);
+                    o2[v] = p.mode2 == 2 ? rs2[v] * (gg - mg[v] - xh2 * mgx2[v]) : gg;
+                }
+                storev<T, V>(dx + row * C + m.cv * V, o);
+                if (dx2) storev<T, V>(dx2 + row * C + m.cv * V, o2);
+            }
+        }
     }
 }
 

@@ -26,6 +26,27 @@ static_assert(kRun * 32 == kCkpt, "R3 chunk must equal the checkpoint interval")
 
 __device__ __forceinline__ int pad_pos(int p) { return p + ((p >> 5) << 2); }
 
+// one reverse position for all states (pairs packed):  mu = a (mu + g C)
+template <int N, int JN>
+__device__ __forceinline__ void ragg_step_chunk(const float *s_C, int q, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
+                                                float2 (&mu)[N / 2]) {
+    const float4 c4 = bc_read4<N>(s_C, q, JN);
+    const float2 a0 = decay2<2 * JN>(__fmul2_rn(dt2, A2[2 * JN]));
+    const float2 a1 = decay2<2 * JN + 1>(__fmul2_rn(dt2, A2[2 * JN + 1]));
+    mu[2 * JN] = __fmul2_rn(a0, __ffma2_rn(g2, f2(c4.x, c4.y), mu[2 * JN]));
+    mu[2 * JN + 1] = __fmul2_rn(a1, __ffma2_rn(g2, f2(c4.z, c4.w), mu[2 * JN + 1]));
+}
+template <int N>
+__device__ __forceinline__ void ragg_step(const float *s_C, int q, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
+                                          float2 (&mu)[N / 2]) {
+    ragg_step_chunk<N, 0>(s_C, q, dt2, g2, A2, mu);
+    ragg_step_chunk<N, 1>(s_C, q, dt2, g2, A2, mu);
+    if (N == 16) {
+        ragg_step_chunk<N, (N == 16 ? 2 : 0)>(s_C, q, dt2, g2, A2, mu);
+        ragg_step_chunk<N, (N == 16 ? 3 : 1)>(s_C, q, dt2, g2, A2, mu);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // R1: reverse aggregate per chunk (lane == channel)
 // ---------------------------------------------------------------------------------------------
@@ -44,11 +65,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
     float *s_z = s_g + kTile * kTile;
     float *s_C = s_z + kTile * kTile;
 
-    float A2[N], mu[N];
+    float2 A2[N / 2], mu[N / 2];                      // state pairs packed for FFMA2
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-        A2[n] = active ? p.A[(int64_t)d * N + n] * kLog2e : 0.f;
-        mu[n] = 0.f;
+    for (int m = 0; m < N / 2; ++m) {
+        A2[m] = active ? f2(p.A[(int64_t)d * N + 2 * m] * kLog2e, p.A[(int64_t)d * N + 2 * m + 1] * kLog2e) : f2(0.f, 0.f);
+        mu[m] = f2(0.f, 0.f);
     }
     const float bias = (active && p.delta_bias) ? p.delta_bias[d] : 0.f;
     float sumdt = 0.f;
@@ -81,17 +102,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
                 const float dt = dd[e];
                 const float g = gg[e];
                 sumdt += dt;
-#pragma unroll
-                for (int jn = 0; jn < N / 4; ++jn) {
-                    const float4 c4 = bc_read4<N>(s_C, q, jn);
-                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int n = 4 * jn + k;
-                        const float a = ex2(dt * A2[n]);
-                        mu[n] = a * fmaf(g, cc[k], mu[n]);
-                    }
-                }
+                ragg_step<N>(s_C, q, f2(dt, dt), f2(g, g), A2, mu);
             }
         }
         __syncwarp();
@@ -99,9 +110,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
     if (active) {
         const int64_t o = (((int64_t)wi.b * p.n_seg + wi.seg) * N) * p.dim + d;
 #pragma unroll
-        for (int n = 0; n < N; ++n) {
-            p.Pb[o + (int64_t)n * p.dim] = ex2(A2[n] * sumdt);
-            p.Mloc[o + (int64_t)n * p.dim] = mu[n];
+        for (int m = 0; m < N / 2; ++m) {
+            p.Pb[o + (int64_t)(2 * m) * p.dim] = ex2(A2[m].x * sumdt);
+            p.Pb[o + (int64_t)(2 * m + 1) * p.dim] = ex2(A2[m].y * sumdt);
+            p.Mloc[o + (int64_t)(2 * m) * p.dim] = mu[m].x;
+            p.Mloc[o + (int64_t)(2 * m + 1) * p.dim] = mu[m].y;
         }
     }
 }

@@ -17,6 +17,56 @@
 namespace smb {
 
 // ---------------------------------------------------------------------------------------------
+// one scan position for all N states of this lane's channel, states packed in pairs (FFMA2 / FMUL2):
+//   a = 2^(dt A2) ; h = a h + (dt u) B          [+ y += C h in the main pass]
+// A compile-time subset of the pairs evaluates the decay on the FMA pipe (decay2<M>), the rest on the MUFU.
+// ---------------------------------------------------------------------------------------------
+template <int N, int JN>
+__device__ __forceinline__ void scan_step_agg_chunk(const float *s_B, int q, float2 dt2, float2 du2, const float2 (&A2)[N / 2],
+                                                    float2 (&h)[N / 2]) {
+    const float4 b4 = bc_read4<N>(s_B, q, JN);
+    const float2 a0 = decay2<2 * JN>(__fmul2_rn(dt2, A2[2 * JN]));
+    const float2 a1 = decay2<2 * JN + 1>(__fmul2_rn(dt2, A2[2 * JN + 1]));
+    h[2 * JN] = __ffma2_rn(a0, h[2 * JN], __fmul2_rn(du2, f2(b4.x, b4.y)));
+    h[2 * JN + 1] = __ffma2_rn(a1, h[2 * JN + 1], __fmul2_rn(du2, f2(b4.z, b4.w)));
+}
+template <int N>
+__device__ __forceinline__ void scan_step_agg(const float *s_B, int q, float2 dt2, float2 du2, const float2 (&A2)[N / 2],
+                                              float2 (&h)[N / 2]) {
+    scan_step_agg_chunk<N, 0>(s_B, q, dt2, du2, A2, h);
+    scan_step_agg_chunk<N, 1>(s_B, q, dt2, du2, A2, h);
+    if (N == 16) {
+        scan_step_agg_chunk<N, (N == 16 ? 2 : 0)>(s_B, q, dt2, du2, A2, h);
+        scan_step_agg_chunk<N, (N == 16 ? 3 : 1)>(s_B, q, dt2, du2, A2, h);
+    }
+}
+template <int N, int JN>
+__device__ __forceinline__ void scan_step_main_chunk(const float *s_B, const float *s_C, int q, float2 dt2, float2 du2,
+                                                     const float2 (&A2)[N / 2], float2 (&h)[N / 2], float2 &y) {
+    const float4 b4 = bc_read4<N>(s_B, q, JN);
+    const float4 c4 = bc_read4<N>(s_C, q, JN);
+    const float2 a0 = decay2<2 * JN>(__fmul2_rn(dt2, A2[2 * JN]));
+    const float2 a1 = decay2<2 * JN + 1>(__fmul2_rn(dt2, A2[2 * JN + 1]));
+    h[2 * JN] = __ffma2_rn(a0, h[2 * JN], __fmul2_rn(du2, f2(b4.x, b4.y)));
+    h[2 * JN + 1] = __ffma2_rn(a1, h[2 * JN + 1], __fmul2_rn(du2, f2(b4.z, b4.w)));
+    y = __ffma2_rn(f2(c4.x, c4.y), h[2 * JN], y);
+    y = __ffma2_rn(f2(c4.z, c4.w), h[2 * JN + 1], y);
+}
+template <int N>
+__device__ __forceinline__ float scan_step_main(const float *s_B, const float *s_C, int q, float2 dt2, float2 du2,
+                                                const float2 (&A2)[N / 2], float2 (&h)[N / 2]) {
+    float2 ya = f2(0.f, 0.f), yb = f2(0.f, 0.f);
+    scan_step_main_chunk<N, 0>(s_B, s_C, q, dt2, du2, A2, h, ya);
+    scan_step_main_chunk<N, 1>(s_B, s_C, q, dt2, du2, A2, h, yb);
+    if (N == 16) {
+        scan_step_main_chunk<N, (N == 16 ? 2 : 0)>(s_B, s_C, q, dt2, du2, A2, h, ya);
+        scan_step_main_chunk<N, (N == 16 ? 3 : 1)>(s_B, s_C, q, dt2, du2, A2, h, yb);
+    }
+    const float2 ys = __fadd2_rn(ya, yb);
+    return ys.x + ys.y;
+}
+
+// ---------------------------------------------------------------------------------------------
 // pass 1
 // ---------------------------------------------------------------------------------------------
 template <typename T, int N>
@@ -33,11 +83,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_agg_kernel(const S
     float *s_dt = s_u + kTile * kTile;
     float *s_B = s_dt + kTile * kTile;
 
-    float A2[N], h[N];
+    float2 A2[N / 2], h[N / 2];                       // state pairs (2m, 2m+1) packed for FFMA2
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-        A2[n] = active ? p.A[(int64_t)d * N + n] * kLog2e : 0.f;
-        h[n] = 0.f;
+    for (int m = 0; m < N / 2; ++m) {
+        A2[m] = active ? f2(p.A[(int64_t)d * N + 2 * m] * kLog2e, p.A[(int64_t)d * N + 2 * m + 1] * kLog2e) : f2(0.f, 0.f);
+        h[m] = f2(0.f, 0.f);
     }
     const float bias = (active && p.delta_bias) ? p.delta_bias[d] : 0.f;
     float sumdt = 0.f;
@@ -65,18 +115,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_agg_kernel(const S
                 const int q = 4 * c + e;
                 const float dt = dd[e];
                 const float du = dt * uu[e];
+                const float2 dt2 = f2(dt, dt), du2 = f2(du, du);
                 sumdt += dt;
-#pragma unroll
-                for (int jn = 0; jn < N / 4; ++jn) {
-                    const float4 b4 = bc_read4<N>(s_B, q, jn);
-                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int n = 4 * jn + k;
-                        const float a = ex2(dt * A2[n]);
-                        h[n] = fmaf(a, h[n], du * bb[k]);
-                    }
-                }
+                scan_step_agg<N>(s_B, q, dt2, du2, A2, h);
             }
         }
         __syncwarp();
@@ -84,9 +125,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_agg_kernel(const S
     if (active) {
         const int64_t o = (((int64_t)wi.b * p.n_seg + wi.seg) * N) * p.dim + d;
 #pragma unroll
-        for (int n = 0; n < N; ++n) {
-            p.P[o + (int64_t)n * p.dim] = ex2(A2[n] * sumdt);
-            p.H[o + (int64_t)n * p.dim] = h[n];
+        for (int m = 0; m < N / 2; ++m) {
+            p.P[o + (int64_t)(2 * m) * p.dim] = ex2(A2[m].x * sumdt);
+            p.P[o + (int64_t)(2 * m + 1) * p.dim] = ex2(A2[m].y * sumdt);
+            p.H[o + (int64_t)(2 * m) * p.dim] = h[m].x;
+            p.H[o + (int64_t)(2 * m + 1) * p.dim] = h[m].y;
         }
     }
 }
@@ -182,13 +225,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
     float *s_B = s_z + kTile * kTile;
     float *s_C = s_B + kTile * N;
 
-    float A2[N], h[N];
+    float2 A2[N / 2], h[N / 2];
     {
         const int64_t o = (((int64_t)wi.b * p.n_seg + wi.seg) * N) * p.dim + d;
 #pragma unroll
-        for (int n = 0; n < N; ++n) {
-            A2[n] = active ? p.A[(int64_t)d * N + n] * kLog2e : 0.f;
-            h[n] = active ? p.hin[o + (int64_t)n * p.dim] : 0.f;
+        for (int m = 0; m < N / 2; ++m) {
+            A2[m] = active ? f2(p.A[(int64_t)d * N + 2 * m] * kLog2e, p.A[(int64_t)d * N + 2 * m + 1] * kLog2e) : f2(0.f, 0.f);
+            h[m] = active ? f2(p.hin[o + (int64_t)(2 * m) * p.dim], p.hin[o + (int64_t)(2 * m + 1) * p.dim]) : f2(0.f, 0.f);
         }
     }
     const float bias = (active && p.delta_bias) ? p.delta_bias[d] : 0.f;
@@ -208,7 +251,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
         if (p.hstates && (j0 % kCkpt) == 0 && active) {
             const int64_t o = (((int64_t)wi.b * (p.nck + 1) + j0 / kCkpt) * N) * p.dim + d;
 #pragma unroll
-            for (int n = 0; n < N; ++n) p.hstates[o + (int64_t)n * p.dim] = h[n];
+            for (int m = 0; m < N / 2; ++m) {
+                p.hstates[o + (int64_t)(2 * m) * p.dim] = h[m].x;
+                p.hstates[o + (int64_t)(2 * m + 1) * p.dim] = h[m].y;
+            }
         }
         fill_tile<T>(s_u, u, p.u_ds, wi.nrows, j0, p.L, p.reverse, lane);
         fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
@@ -233,23 +279,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
                 const int q = 4 * c + e;
                 const float dt = dd[e];
                 const float du = dt * uu[e];
-                float y0 = 0.f, y1 = 0.f;
-#pragma unroll
-                for (int jn = 0; jn < N / 4; ++jn) {
-                    const float4 b4 = bc_read4<N>(s_B, q, jn);
-                    const float4 c4 = bc_read4<N>(s_C, q, jn);
-                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int n = 4 * jn + k;
-                        const float a = ex2(dt * A2[n]);
-                        h[n] = fmaf(a, h[n], du * bb[k]);
-                        if (k & 1) y1 = fmaf(cc[k], h[n], y1);
-                        else y0 = fmaf(cc[k], h[n], y0);
-                    }
-                }
-                const float y = fmaf(Dv, uu[e], y0 + y1);
+                const float ys = scan_step_main<N>(s_B, s_C, q, f2(dt, dt), f2(du, du), A2, h);
+                const float y = fmaf(Dv, uu[e], ys);
                 yy[e] = y;
                 yz[e] = y * zz[e];                                  // zz already holds silu(z)
             }
@@ -265,7 +296,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
     if (p.hstates && j_end == p.L && active) {
         const int64_t o = (((int64_t)wi.b * (p.nck + 1) + p.nck) * N) * p.dim + d;
 #pragma unroll
-        for (int n = 0; n < N; ++n) p.hstates[o + (int64_t)n * p.dim] = h[n];
+        for (int m = 0; m < N / 2; ++m) {
+            p.hstates[o + (int64_t)(2 * m) * p.dim] = h[m].x;
+            p.hstates[o + (int64_t)(2 * m + 1) * p.dim] = h[m].y;
+        }
     }
 }
 

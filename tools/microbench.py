@@ -57,10 +57,12 @@ def main():
     ap.add_argument("--dtypes", default="f32,bf16")
     ap.add_argument("--batches", default="1,2")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "microbench.json"))
+    ap.add_argument("--stages", default="0,1,2,3")
+    ap.add_argument("--no-ref", action="store_true")
     args = ap.parse_args()
     from segmamba_b200 import causal_conv1d_cuda as cc
     from segmamba_b200 import selective_scan_cuda as ssc
-    ref_ss, ref_cc = load_ref("selective_scan_cuda"), load_ref("causal_conv1d_cuda")
+    ref_ss, ref_cc = (None, None) if args.no_ref else (load_ref("selective_scan_cuda"), load_ref("causal_conv1d_cuda"))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -75,7 +77,7 @@ def main():
         dt = dts[dname]
         s = torch.empty(0, dtype=dt).element_size()
         for batch in [int(b) for b in args.batches.split(",")]:
-            for D, L in STAGES:
+            for D, L in [STAGES[int(i)] for i in args.stages.split(",")]:
                 torch.manual_seed(0)
                 u = torch.randn(batch, D, L, device=dev).to(dt)
                 delta = (0.5 * torch.randn(batch, D, L, device=dev)).to(dt)
