@@ -263,6 +263,87 @@ __device__ __forceinline__ void prepass_gate_grad(float *gtile, const float *zti
 }
 
 // ---------------------------------------------------------------------------------------------
+// Batched fills.  The recurrence kernels are latency-sensitive (3-4 resident warps per scheduler), so the global
+// loads of ALL streams of a tile are issued back to back into registers (raw, unconverted) before the first
+// conversion / shared store: one DRAM/L2 latency per tile instead of one per stream.  The next tile's lines are
+// pulled into L2 with prefetch.global.L2 while the current tile is being computed.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Raw4 { using type = uint2; };
+template <> struct Raw4<float> { using type = float4; };
+template <typename T> __device__ __forceinline__ typename Raw4<T>::type ldraw4(const T *p) {
+    return *reinterpret_cast<const typename Raw4<T>::type *>(p);
+}
+template <typename T> __device__ __forceinline__ typename Raw4<T>::type zeroraw4();
+template <> __device__ __forceinline__ float4 zeroraw4<float>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <> __device__ __forceinline__ uint2 zeroraw4<__half>() { return make_uint2(0u, 0u); }
+template <> __device__ __forceinline__ uint2 zeroraw4<__nv_bfloat16>() { return make_uint2(0u, 0u); }
+template <typename T> __device__ __forceinline__ float4 cvtraw4(typename Raw4<T>::type r);
+template <> __device__ __forceinline__ float4 cvtraw4<float>(float4 r) { return r; }
+template <> __device__ __forceinline__ float4 cvtraw4<__half>(uint2 r) {
+    const float2 a = __half22float2(*reinterpret_cast<__half2 *>(&r.x)), b = __half22float2(*reinterpret_cast<__half2 *>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 cvtraw4<__nv_bfloat16>(uint2 r) {      // bf16 -> fp32 is a 16-bit shift
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// true when 4-element vector accesses of a (rows, L) operand are aligned for every full tile of this walk
+template <typename T> __device__ __forceinline__ bool stream_aligned(const T *base, int64_t row_stride, int L, bool reverse) {
+    return aligned4(base) && (row_stride & 3) == 0 && (!reverse || (L & 3) == 0);
+}
+
+// fill K activation tiles with scan positions [j0, j0+32); REQUIRES j0 + 32 <= L and stream_aligned() for every stream
+template <typename T, int K, int KA>
+__device__ __forceinline__ void fill_tiles_fast(float *const (&tiles)[KA], const T *const (&bases)[KA], const int64_t (&strides)[KA],
+                                                int nrows, int j0, int L, bool reverse, int lane) {
+    static_assert(K <= KA, "array too small");
+    constexpr int H = sizeof(T) == 4 ? 2 : 1;            // fp32: two halves to bound the registers in flight
+    constexpr int IT = 8 / H;
+#pragma unroll
+    for (int half = 0; half < H; ++half) {
+        typename Raw4<T>::type r[K][IT];
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+            const int unit = (half * IT + i) * 32 + lane;
+            const int row = unit >> 3, c = unit & 7;
+            const int tok = reverse ? L - 4 - (j0 + 4 * c) : j0 + 4 * c;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                r[k][i] = row < nrows ? ldraw4<T>(bases[k] + (int64_t)row * strides[k] + tok) : zeroraw4<T>();
+        }
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+            const int unit = (half * IT + i) * 32 + lane;
+            const int row = unit >> 3, c = unit & 7;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float4 v = cvtraw4<T>(r[k][i]);
+                if (reverse) v = make_float4(v.w, v.z, v.y, v.x);
+                tile_write4(tiles[k], row, c, v);
+            }
+        }
+    }
+}
+
+// pull the next tile's row segments into L2 (one or two lines per row and stream)
+template <typename T, int K, int KA>
+__device__ __forceinline__ void prefetch_tiles(const T *const (&bases)[KA], const int64_t (&strides)[KA], int nrows, int j0n, int L,
+                                               bool reverse, int lane) {
+    if (lane < nrows && j0n < L) {
+        const int lo = reverse ? max(L - j0n - kTile, 0) : j0n;
+        const int hi = reverse ? L - 1 - j0n : min(j0n + kTile, L) - 1;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const T *rp = bases[k] + (int64_t)lane * strides[k];
+            prefetch_l2(rp + lo);
+            if (sizeof(T) == 4) prefetch_l2(rp + hi);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Warp-private B / C tile: 32 scan positions x N states, position-major so that one position's
 // states are read with broadcast LDS.128 by every lane (lane == channel).  The 16-byte chunk
 // index is XOR-swizzled with (q>>1) to spread the transposing fill over 8 bank groups.
@@ -341,6 +422,36 @@ __device__ __forceinline__ void store_run8(T *row, int j, int L, bool reverse, c
 #pragma unroll
             for (int i = 0; i < kRun; ++i) if (th - i >= 0) row[th - i] = from_f32<T>(v[i]);
         }
+    }
+}
+
+// K (1 or 2) B/C tiles at once: all 2*N (or N) global loads in flight before the first shared store
+template <typename T, int N, int K>
+__device__ __forceinline__ void fill_bc_tiles(float *const (&tiles)[K], const T *const (&bases)[K], const int64_t (&ns)[K],
+                                              const int64_t (&ls)[K], int j0, int L, bool reverse, int lane) {
+    const int j = j0 + lane;
+    const bool valid = j < L;
+    const int tok = pos_to_tok(valid ? j : 0, L, reverse);
+    T v[K][N];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const T *b = bases[k] + (int64_t)tok * ls[k];
+#pragma unroll
+        for (int n = 0; n < N; ++n) v[k][n] = valid ? b[(int64_t)n * ns[k]] : from_f32<T>(0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) tiles[k][bc_off<N>(lane, n)] = to_f32<T>(v[k][n]);
+    }
+}
+template <typename T, int N, int K>
+__device__ __forceinline__ void prefetch_bc(const T *const (&bases)[K], const int64_t (&ns)[K], const int64_t (&ls)[K], int j0n, int L,
+                                            bool reverse, int lane) {
+    if (lane < N && j0n < L) {
+        const int lo = reverse ? max(L - j0n - kTile, 0) : j0n;
+#pragma unroll
+        for (int k = 0; k < K; ++k) prefetch_l2(bases[k] + (int64_t)lane * ns[k] + (int64_t)lo * ls[k]);
     }
 }
 

@@ -82,11 +82,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
     const int j_begin = wi.seg * kCkpt;
     const int j_end = min(p.L, j_begin + kCkpt);
     const int last_tile = j_begin + ((j_end - j_begin - 1) / kTile) * kTile;
+    const bool fast = stream_aligned(dl, p.delta_ds, p.L, p.reverse) && stream_aligned(go, p.dout_ds, p.L, p.reverse) &&
+                      (!kHasZ || stream_aligned(z, p.z_ds, p.L, p.reverse));
     for (int j0 = last_tile; j0 >= j_begin; j0 -= kTile) {
-        fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
-        fill_tile<T>(s_g, go, p.dout_ds, wi.nrows, j0, p.L, p.reverse, lane);
-        if (kHasZ) fill_tile<T>(s_z, z, p.z_ds, wi.nrows, j0, p.L, p.reverse, lane);
-        fill_bc_tile<T, N>(s_C, Cm, p.C_ns, p.C_ls, j0, p.L, p.reverse, lane);
+        {
+            constexpr int K = kHasZ ? 3 : 2;
+            const T *const bases[3] = {dl, go, kHasZ ? z : dl};
+            const int64_t strides[3] = {p.delta_ds, p.dout_ds, kHasZ ? p.z_ds : p.delta_ds};
+            if (fast && j0 + kTile <= p.L) {
+                float *const tiles[3] = {s_dt, s_g, s_z};
+                fill_tiles_fast<T, K, 3>(tiles, bases, strides, wi.nrows, j0, p.L, p.reverse, lane);
+            } else {
+                fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
+                fill_tile<T>(s_g, go, p.dout_ds, wi.nrows, j0, p.L, p.reverse, lane);
+                if (kHasZ) fill_tile<T>(s_z, z, p.z_ds, wi.nrows, j0, p.L, p.reverse, lane);
+            }
+            float *const bt[1] = {s_C};
+            const T *const bb[1] = {Cm};
+            const int64_t bns[1] = {p.C_ns}, bls[1] = {p.C_ls};
+            fill_bc_tiles<T, N, 1>(bt, bb, bns, bls, j0, p.L, p.reverse, lane);
+            if (j0 - kTile >= j_begin) {
+                prefetch_tiles<T, K, 3>(bases, strides, wi.nrows, j0 - kTile, p.L, p.reverse, lane);
+                prefetch_bc<T, N, 1>(bb, bns, bls, j0 - kTile, p.L, p.reverse, lane);
+            }
+        }
         __syncwarp();
         prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions: a = 1, and g == 0 there
         if (kHasZ) prepass_gate_grad(s_g, s_z, lane);
@@ -161,7 +180,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const Sca
     }
 
     // ---- per-lane runs ----
-    float dt[kRun], uu[kRun], gg[kRun], sLB[kRun], sAq[kRun], yy[kRun];
+    float dt[kRun], uu[kRun], gg[kRun];
     float bias = 0.f, Dv = 0.f;
     if (active) {
         bias = p.delta_bias ? p.delta_bias[d] : 0.f;
@@ -189,42 +208,59 @@ __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const Sca
 #pragma unroll
         for (int i = 0; i < kRun; ++i) { dt[i] = 0.f; uu[i] = 0.f; gg[i] = 0.f; }
     }
-#pragma unroll
-    for (int i = 0; i < kRun; ++i) { sLB[i] = 0.f; sAq[i] = 0.f; yy[i] = 0.f; }
-
     __syncthreads();   // B/C tiles ready
 
-    const int64_t hs_off = (int64_t)b * p.hs_bs + ((int64_t)chunk * N) * p.dim + d;
-    const int64_t mi_off = (((int64_t)b * p.nck + chunk) * N) * p.dim + d;
     const int bo = pad_pos(lane * kRun);               // this lane's run inside a padded row
     float *myB = slabB + warp * kRowPad + bo;
     float *myC = slabC + warp * kRowPad + bo;
 
+    // per-state scalars of this channel, loaded once: lane n holds (A2, h_in, m_in) of state n, broadcast by shuffle
+    float A2_l = 0.f, hin_l = 0.f, min_l = 0.f;
+    if (active && lane < N) {
+        A2_l = p.A[(int64_t)d * N + lane] * kLog2e;
+        hin_l = p.hs[(int64_t)b * p.hs_bs + ((int64_t)chunk * N + lane) * p.dim + d];
+        min_l = p.Min[(((int64_t)b * p.nck + chunk) * N + lane) * p.dim + d];
+    }
+    // item pairs (2j, 2j+1) packed for FFMA2
+    float2 dt2[kRun / 2], dtu2[kRun / 2], g2[kRun / 2], sLB2[kRun / 2], sAq2[kRun / 2], yy2[kRun / 2];
+#pragma unroll
+    for (int j = 0; j < kRun / 2; ++j) {
+        dt2[j] = f2(dt[2 * j], dt[2 * j + 1]);
+        dtu2[j] = f2(dt[2 * j] * uu[2 * j], dt[2 * j + 1] * uu[2 * j + 1]);
+        g2[j] = f2(gg[2 * j], gg[2 * j + 1]);
+        sLB2[j] = f2(0.f, 0.f); sAq2[j] = f2(0.f, 0.f); yy2[j] = f2(0.f, 0.f);
+    }
+
 #pragma unroll 1
     for (int n = 0; n < N; ++n) {
-        float dBv[kRun], dCv[kRun];
+        float2 dB2[kRun / 2], dC2[kRun / 2];
+        const float A2n = __shfl_sync(0xffffffffu, A2_l, n);
+        const float h_in = __shfl_sync(0xffffffffu, hin_l, n);
+        const float m_in = __shfl_sync(0xffffffffu, min_l, n);
         if (active) {
-            const float A2n = p.A[(int64_t)d * N + n] * kLog2e;
-            const float h_in = p.hs[hs_off + (int64_t)n * p.dim];
-            const float m_in = p.Min[mi_off + (int64_t)n * p.dim];
-            float Bv[kRun], Cv[kRun];
+            float2 Bv2[kRun / 2], Cv2[kRun / 2];
             {
                 const float4 b0 = *reinterpret_cast<const float4 *>(sB + n * kRowPad + bo);
                 const float4 b1 = *reinterpret_cast<const float4 *>(sB + n * kRowPad + bo + 4);
                 const float4 c0 = *reinterpret_cast<const float4 *>(sC + n * kRowPad + bo);
                 const float4 c1 = *reinterpret_cast<const float4 *>(sC + n * kRowPad + bo + 4);
-                Bv[0] = b0.x; Bv[1] = b0.y; Bv[2] = b0.z; Bv[3] = b0.w; Bv[4] = b1.x; Bv[5] = b1.y; Bv[6] = b1.z; Bv[7] = b1.w;
-                Cv[0] = c0.x; Cv[1] = c0.y; Cv[2] = c0.z; Cv[3] = c0.w; Cv[4] = c1.x; Cv[5] = c1.y; Cv[6] = c1.z; Cv[7] = c1.w;
+                Bv2[0] = f2(b0.x, b0.y); Bv2[1] = f2(b0.z, b0.w); Bv2[2] = f2(b1.x, b1.y); Bv2[3] = f2(b1.z, b1.w);
+                Cv2[0] = f2(c0.x, c0.y); Cv2[1] = f2(c0.z, c0.w); Cv2[2] = f2(c1.x, c1.y); Cv2[3] = f2(c1.z, c1.w);
             }
-            float a[kRun], bb[kRun], hs[kRun];
-            // lane aggregates of the forward recurrence
+            const float2 A2n2 = f2(A2n, A2n);
+            float2 a2[kRun / 2], bb2[kRun / 2], gc2[kRun / 2], hs2[kRun / 2], lam2[kRun / 2];
+#pragma unroll
+            for (int j = 0; j < kRun / 2; ++j) {
+                a2[j] = ex2x2_mufu(__fmul2_rn(dt2[j], A2n2));
+                bb2[j] = __fmul2_rn(dtu2[j], Bv2[j]);
+                gc2[j] = __fmul2_rn(g2[j], Cv2[j]);
+            }
+            // lane aggregates of the forward recurrence (sequential over the 8 positions)
             float Aagg = 1.f, Hagg = 0.f;
 #pragma unroll
-            for (int i = 0; i < kRun; ++i) {
-                a[i] = ex2(dt[i] * A2n);
-                bb[i] = dt[i] * uu[i] * Bv[i];
-                Hagg = fmaf(a[i], Hagg, bb[i]);
-                Aagg *= a[i];
+            for (int j = 0; j < kRun / 2; ++j) {
+                Hagg = fmaf(a2[j].x, Hagg, bb2[j].x); Aagg *= a2[j].x;
+                Hagg = fmaf(a2[j].y, Hagg, bb2[j].y); Aagg *= a2[j].y;
             }
             // exclusive forward warp scan -> state entering this lane's run
             float As = Aagg, Hs = Hagg;
@@ -237,11 +273,17 @@ __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const Sca
             if (lane == 0) { Ae = 1.f; He = 0.f; }
             float h = fmaf(Ae, h_in, He);
 #pragma unroll
-            for (int i = 0; i < kRun; ++i) { h = fmaf(a[i], h, bb[i]); hs[i] = h; }
+            for (int j = 0; j < kRun / 2; ++j) {
+                h = fmaf(a2[j].x, h, bb2[j].x); hs2[j].x = h;
+                h = fmaf(a2[j].y, h, bb2[j].y); hs2[j].y = h;
+            }
             // lane aggregates of the reverse (adjoint) recurrence  mu_i = a_i (mu_{i+1} + g_i C_i)
             float Magg = 0.f;
 #pragma unroll
-            for (int i = kRun - 1; i >= 0; --i) Magg = a[i] * fmaf(gg[i], Cv[i], Magg);
+            for (int j = kRun / 2 - 1; j >= 0; --j) {
+                Magg = a2[j].y * (Magg + gc2[j].y);
+                Magg = a2[j].x * (Magg + gc2[j].x);
+            }
             float Ar = Aagg, Mr = Magg;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -251,24 +293,35 @@ __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const Sca
             float Ax = __shfl_down_sync(0xffffffffu, Ar, 1), Mx = __shfl_down_sync(0xffffffffu, Mr, 1);
             if (lane == 31) { Ax = 1.f; Mx = 0.f; }
             float m = fmaf(Ax, m_in, Mx);                // mu entering this run from the right
-            float dAacc = 0.f;
 #pragma unroll
-            for (int i = kRun - 1; i >= 0; --i) {
-                const float lam = fmaf(gg[i], Cv[i], m);
-                m = a[i] * lam;
-                yy[i] = fmaf(Cv[i], hs[i], yy[i]);
-                dCv[i] = gg[i] * hs[i];
-                dBv[i] = lam * dt[i] * uu[i];
-                sLB[i] = fmaf(lam, Bv[i], sLB[i]);
-                const float qv = lam * (hs[i] - bb[i]);
-                dAacc = fmaf(dt[i], qv, dAacc);
-                sAq[i] = fmaf(A2n, qv, sAq[i]);
+            for (int j = kRun / 2 - 1; j >= 0; --j) {
+                lam2[j].y = gc2[j].y + m; m = a2[j].y * lam2[j].y;
+                lam2[j].x = gc2[j].x + m; m = a2[j].x * lam2[j].x;
             }
-            dAacc = warp_sum(dAacc);                    // dA_n = sum_t lambda dt (h - b)
+            // element-wise gradient terms, two positions per instruction
+            float2 dA2 = f2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < kRun / 2; ++j) {
+                yy2[j] = __ffma2_rn(Cv2[j], hs2[j], yy2[j]);
+                dC2[j] = __fmul2_rn(g2[j], hs2[j]);
+                dB2[j] = __fmul2_rn(lam2[j], dtu2[j]);
+                sLB2[j] = __ffma2_rn(lam2[j], Bv2[j], sLB2[j]);
+                const float2 hm = __ffma2_rn(bb2[j], f2(-1.f, -1.f), hs2[j]);     // h - b = a h_prev
+                const float2 qv = __fmul2_rn(lam2[j], hm);
+                dA2 = __ffma2_rn(dt2[j], qv, dA2);
+                sAq2[j] = __ffma2_rn(A2n2, qv, sAq2[j]);
+            }
+            const float dAacc = warp_sum(dA2.x + dA2.y);          // dA_n = sum_t lambda dt (h - b)
             if (lane == 0) atomicAdd(p.dA + (int64_t)d * N + n, dAacc);
         } else {
 #pragma unroll
-            for (int i = 0; i < kRun; ++i) { dBv[i] = 0.f; dCv[i] = 0.f; }
+            for (int j = 0; j < kRun / 2; ++j) { dB2[j] = f2(0.f, 0.f); dC2[j] = f2(0.f, 0.f); }
+        }
+        float dBv[kRun], dCv[kRun];
+#pragma unroll
+        for (int j = 0; j < kRun / 2; ++j) {
+            dBv[2 * j] = dB2[j].x; dBv[2 * j + 1] = dB2[j].y;
+            dCv[2 * j] = dC2[j].x; dCv[2 * j + 1] = dC2[j].y;
         }
         // ---- reduce dB / dC over the CTA's channels ----
         *reinterpret_cast<float4 *>(myB) = make_float4(dBv[0], dBv[1], dBv[2], dBv[3]);
@@ -296,6 +349,13 @@ __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const Sca
     }
 
     if (!active) return;
+    float sLB[kRun], sAq[kRun], yy[kRun];
+#pragma unroll
+    for (int j = 0; j < kRun / 2; ++j) {
+        sLB[2 * j] = sLB2[j].x; sLB[2 * j + 1] = sLB2[j].y;
+        sAq[2 * j] = sAq2[j].x; sAq[2 * j + 1] = sAq2[j].y;
+        yy[2 * j] = yy2[j].x; yy[2 * j + 1] = yy2[j].y;
+    }
     // ---- epilogue: du, ddelta, dz, (out_z), dD, ddelta_bias ----
     float duv[kRun], ddv[kRun];
     float dDacc = 0.f, dbacc = 0.f;

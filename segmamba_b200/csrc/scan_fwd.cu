@@ -98,10 +98,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_agg_kernel(const S
 
     const int j_begin = wi.seg * p.S;
     const int j_end = min(p.L, j_begin + p.S);
+    const bool fast = stream_aligned(u, p.u_ds, p.L, p.reverse) && stream_aligned(dl, p.delta_ds, p.L, p.reverse);
     for (int j0 = j_begin; j0 < j_end; j0 += kTile) {
-        fill_tile<T>(s_u, u, p.u_ds, wi.nrows, j0, p.L, p.reverse, lane);
-        fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
-        fill_bc_tile<T, N>(s_B, Bm, p.B_ns, p.B_ls, j0, p.L, p.reverse, lane);
+        {
+            float *const tiles[2] = {s_u, s_dt};
+            const T *const bases[2] = {u, dl};
+            const int64_t strides[2] = {p.u_ds, p.delta_ds};
+            if (fast && j0 + kTile <= p.L) {
+                fill_tiles_fast<T, 2, 2>(tiles, bases, strides, wi.nrows, j0, p.L, p.reverse, lane);
+            } else {
+                fill_tile<T>(s_u, u, p.u_ds, wi.nrows, j0, p.L, p.reverse, lane);
+                fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
+            }
+            float *const bt[1] = {s_B};
+            const T *const bb[1] = {Bm};
+            const int64_t bns[1] = {p.B_ns}, bls[1] = {p.B_ls};
+            fill_bc_tiles<T, N, 1>(bt, bb, bns, bls, j0, p.L, p.reverse, lane);
+            if (j0 + kTile < j_end) {
+                prefetch_tiles<T, 2, 2>(bases, strides, wi.nrows, j0 + kTile, p.L, p.reverse, lane);
+                prefetch_bc<T, N, 1>(bb, bns, bls, j0 + kTile, p.L, p.reverse, lane);
+            }
+        }
         __syncwarp();
         prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions become scan identities
 #pragma unroll 2
@@ -247,6 +264,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
 
     const int j_begin = wi.seg * p.S;
     const int j_end = min(p.L, j_begin + p.S);
+    const bool fast = stream_aligned(u, p.u_ds, p.L, p.reverse) && stream_aligned(dl, p.delta_ds, p.L, p.reverse) &&
+                      (!kHasZ || stream_aligned(z, p.z_ds, p.L, p.reverse));
     for (int j0 = j_begin; j0 < j_end; j0 += kTile) {
         if (p.hstates && (j0 % kCkpt) == 0 && active) {
             const int64_t o = (((int64_t)wi.b * (p.nck + 1) + j0 / kCkpt) * N) * p.dim + d;
@@ -256,11 +275,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
                 p.hstates[o + (int64_t)(2 * m + 1) * p.dim] = h[m].y;
             }
         }
-        fill_tile<T>(s_u, u, p.u_ds, wi.nrows, j0, p.L, p.reverse, lane);
-        fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
-        if (kHasZ) fill_tile<T>(s_z, z, p.z_ds, wi.nrows, j0, p.L, p.reverse, lane);
-        fill_bc_tile<T, N>(s_B, Bm, p.B_ns, p.B_ls, j0, p.L, p.reverse, lane);
-        fill_bc_tile<T, N>(s_C, Cm, p.C_ns, p.C_ls, j0, p.L, p.reverse, lane);
+        {
+            constexpr int K = kHasZ ? 3 : 2;
+            float *const tiles[3] = {s_u, s_dt, s_z};
+            const T *const bases[3] = {u, dl, kHasZ ? z : u};
+            const int64_t strides[3] = {p.u_ds, p.delta_ds, kHasZ ? p.z_ds : p.u_ds};
+            if (fast && j0 + kTile <= p.L) {
+                fill_tiles_fast<T, K, 3>(tiles, bases, strides, wi.nrows, j0, p.L, p.reverse, lane);
+            } else {
+                fill_tile<T>(s_u, u, p.u_ds, wi.nrows, j0, p.L, p.reverse, lane);
+                fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
+                if (kHasZ) fill_tile<T>(s_z, z, p.z_ds, wi.nrows, j0, p.L, p.reverse, lane);
+            }
+            float *const bt[2] = {s_B, s_C};
+            const T *const bb[2] = {Bm, Cm};
+            const int64_t bns[2] = {p.B_ns, p.C_ns}, bls[2] = {p.B_ls, p.C_ls};
+            fill_bc_tiles<T, N, 2>(bt, bb, bns, bls, j0, p.L, p.reverse, lane);
+            if (j0 + kTile < j_end) {
+                prefetch_tiles<T, K, 3>(bases, strides, wi.nrows, j0 + kTile, p.L, p.reverse, lane);
+                prefetch_bc<T, N, 2>(bb, bns, bls, j0 + kTile, p.L, p.reverse, lane);
+            }
+        }
         __syncwarp();
         prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions become scan identities
         if (kHasZ) prepass_silu(s_z, lane);
