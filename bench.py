@@ -247,6 +247,11 @@ def main_native(args):
     for _ in range(W):
         step(x_dev, y_dev)
     barrier()
+    # host-side enqueue time of one step (no synchronisation inside): tells how close the step is to launch-bound
+    t0 = time.perf_counter()
+    step(x_dev, y_dev)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
 
     sampler = ClockSampler(local_rank)
     launches0 = _lib.launch_count()
@@ -306,6 +311,7 @@ def main_native(args):
             "roofline": roofline,
             "roofline_scan_bwd": roof_bwd,
             "native_ms_per_step": native_ms,
+            "host_enqueue_ms_per_step": host_ms,
         }
         if world == 1 and not args.no_cpu_baseline:
             res = run_cpu(1, 0, args.cpu_sample)

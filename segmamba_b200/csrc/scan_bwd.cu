@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const Sca
     const bool rev = p.reverse;
     const int L = p.L;
 
-    // ---- stage B and C for the chunk: thread t <-> position jc + t ----
+    // ---- stage B and C for the chunk: thread t <-> position jc + t; all 2N loads in flight before the first store ----
     {
         const T *Bm = reinterpret_cast<const T *>(p.B) + b * p.B_bs + (int64_t)g * p.B_gs;
         const T *Cm = reinterpret_cast<const T *>(p.C) + b * p.C_bs + (int64_t)g * p.C_gs;
@@ -172,10 +172,16 @@ __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const Sca
         const bool valid = j < L;
         const int tok = pos_to_tok(valid ? j : 0, L, rev);
         const int so = pad_pos(t);
-#pragma unroll 4
+        T vb[N], vc[N];
+#pragma unroll
         for (int n = 0; n < N; ++n) {
-            sB[n * kRowPad + so] = valid ? to_f32<T>(Bm[(int64_t)n * p.B_ns + (int64_t)tok * p.B_ls]) : 0.f;
-            sC[n * kRowPad + so] = valid ? to_f32<T>(Cm[(int64_t)n * p.C_ns + (int64_t)tok * p.C_ls]) : 0.f;
+            vb[n] = valid ? Bm[(int64_t)n * p.B_ns + (int64_t)tok * p.B_ls] : from_f32<T>(0.f);
+            vc[n] = valid ? Cm[(int64_t)n * p.C_ns + (int64_t)tok * p.C_ls] : from_f32<T>(0.f);
+        }
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            sB[n * kRowPad + so] = to_f32<T>(vb[n]);
+            sC[n * kRowPad + so] = to_f32<T>(vc[n]);
         }
     }
 
@@ -334,11 +340,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const Sca
             const int j = jc + t;
             if (j < L) {
                 const int so = pad_pos(t);
-                float sb = 0.f, sc = 0.f;
-                for (int w2 = 0; w2 < nch; ++w2) {
-                    sb += slabB[w2 * kRowPad + so];
-                    sc += slabC[w2 * kRowPad + so];
+                float vb[kBwdWarps], vc[kBwdWarps];   // inactive warps wrote zeros: fixed trip count, loads first
+#pragma unroll
+                for (int w2 = 0; w2 < kBwdWarps; ++w2) {
+                    vb[w2] = slabB[w2 * kRowPad + so];
+                    vc[w2] = slabC[w2 * kRowPad + so];
                 }
+                const float sb = ((vb[0] + vb[1]) + (vb[2] + vb[3])) + ((vb[4] + vb[5]) + (vb[6] + vb[7]));
+                const float sc = ((vc[0] + vc[1]) + (vc[2] + vc[3])) + ((vc[4] + vc[5]) + (vc[6] + vc[7]));
                 const int tok = pos_to_tok(j, L, rev);
                 const int64_t o = (((int64_t)b * p.G + g) * N + n) * (int64_t)L + tok;
                 atomicAdd(p.dB + o, sb);
