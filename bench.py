@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--channels-last", action="store_true", help="channels_last_3d activations for the conv stack")
-    ap.add_argument("--cpu-sample", type=int, default=64, help="edge of the cubic crop the CPU arm runs per step")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="edge of the cubic crop the CPU arm runs per step")
     return ap.parse_args()
 
 
