@@ -68,11 +68,21 @@ template <int M> __device__ __forceinline__ float2 decay2(float2 arg) {
     return ex2x2_mufu(arg);
 }
 
-// softplus with the reference's threshold (selective_scan_fwd_kernel.cuh:155); select, not branch, so that a run of
-// positions can be processed as straight-line code
+// softplus with the reference's threshold (selective_scan_fwd_kernel.cuh:155), branch-free and ~14 instructions:
+//   softplus(x) = max(x, 0) + log1p(t),  t = exp(-|x|) in (0, 1]
+//   log1p(t)    = 2 atanh(s),  s = t / (2 + t) <= 1/3  ->  2 s (1 + w/3 + w^2/5 + ... + w^6/13),  w = s^2
+// (series remainder < 2e-8 relative; for x > 20 the log term is < 2.1e-9, i.e. the reference's `x` branch in fp32).
 __device__ __forceinline__ float softplus20(float x) {
-    const float sp = log1pf(__expf(fminf(x, 20.f)));
-    return x <= 20.f ? sp : x;
+    const float t = __expf(-fabsf(x));
+    const float s = __fdividef(t, 2.f + t);
+    const float w = s * s;
+    float p = fmaf(w, 1.f / 13.f, 1.f / 11.f);
+    p = fmaf(p, w, 1.f / 9.f);
+    p = fmaf(p, w, 1.f / 7.f);
+    p = fmaf(p, w, 1.f / 5.f);
+    p = fmaf(p, w, 1.f / 3.f);
+    p = fmaf(p, w, 1.f);
+    return fmaf(2.f * s, p, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
@@ -350,6 +360,10 @@ __device__ __forceinline__ void prefetch_tiles(const T *const (&bases)[KA], cons
 // ---------------------------------------------------------------------------------------------
 template <int N> __device__ __forceinline__ int bc_off(int q, int n) {
     return q * N + ((((n >> 2) ^ ((q >> 1) & (N / 4 - 1)))) << 2) + (n & 3);
+}
+// same, for a position known at compile time relative to a block of 8 positions (blk = tile + 8*k*N): constant offset
+template <int N, int QL, int CH> __device__ __forceinline__ float4 bc_read4_c(const float *blk) {
+    return *reinterpret_cast<const float4 *>(blk + QL * N + (((CH ^ ((QL >> 1) & (N / 4 - 1)))) << 2));
 }
 template <int N> __device__ __forceinline__ float4 bc_read4(const float *tile, int q, int chunk) {
     return *reinterpret_cast<const float4 *>(tile + q * N + (((chunk ^ ((q >> 1) & (N / 4 - 1)))) << 2));

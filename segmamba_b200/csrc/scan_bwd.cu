@@ -27,23 +27,34 @@ static_assert(kRun * 32 == kCkpt, "R3 chunk must equal the checkpoint interval")
 __device__ __forceinline__ int pad_pos(int p) { return p + ((p >> 5) << 2); }
 
 // one reverse position for all states (pairs packed):  mu = a (mu + g C)
-template <int N, int JN>
-__device__ __forceinline__ void ragg_step_chunk(const float *s_C, int q, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
+template <int N, int QL, int JN>
+__device__ __forceinline__ void ragg_step_chunk(const float *s_C, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
                                                 float2 (&mu)[N / 2]) {
-    const float4 c4 = bc_read4<N>(s_C, q, JN);
+    const float4 c4 = bc_read4_c<N, QL, JN>(s_C);
     const float2 a0 = decay2<2 * JN>(__fmul2_rn(dt2, A2[2 * JN]));
     const float2 a1 = decay2<2 * JN + 1>(__fmul2_rn(dt2, A2[2 * JN + 1]));
     mu[2 * JN] = __fmul2_rn(a0, __ffma2_rn(g2, f2(c4.x, c4.y), mu[2 * JN]));
     mu[2 * JN + 1] = __fmul2_rn(a1, __ffma2_rn(g2, f2(c4.z, c4.w), mu[2 * JN + 1]));
 }
-template <int N>
-__device__ __forceinline__ void ragg_step(const float *s_C, int q, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
+template <int N, int QL>
+__device__ __forceinline__ void ragg_step(const float *s_C, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
                                           float2 (&mu)[N / 2]) {
-    ragg_step_chunk<N, 0>(s_C, q, dt2, g2, A2, mu);
-    ragg_step_chunk<N, 1>(s_C, q, dt2, g2, A2, mu);
+    ragg_step_chunk<N, QL, 0>(s_C, dt2, g2, A2, mu);
+    ragg_step_chunk<N, QL, 1>(s_C, dt2, g2, A2, mu);
     if (N == 16) {
-        ragg_step_chunk<N, (N == 16 ? 2 : 0)>(s_C, q, dt2, g2, A2, mu);
-        ragg_step_chunk<N, (N == 16 ? 3 : 1)>(s_C, q, dt2, g2, A2, mu);
+        ragg_step_chunk<N, QL, (N == 16 ? 2 : 0)>(s_C, dt2, g2, A2, mu);
+        ragg_step_chunk<N, QL, (N == 16 ? 3 : 1)>(s_C, dt2, g2, A2, mu);
+    }
+}
+// 8 consecutive positions walked in descending order (compile-time local index QL = 7..0)
+template <int N, int QL>
+__device__ __forceinline__ void ragg_block(const float *blkC, const float (&gg)[8], const float (&dd)[8], const float2 (&A2)[N / 2],
+                                           float2 (&mu)[N / 2], float &sumdt) {
+    if constexpr (QL >= 0) {
+        const float dt = dd[QL], g = gg[QL];
+        sumdt += dt;
+        ragg_step<N, QL>(blkC, f2(dt, dt), f2(g, g), A2, mu);
+        ragg_block<N, QL - 1>(blkC, gg, dd, A2, mu, sumdt);
     }
 }
 
@@ -109,20 +120,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
         __syncwarp();
         prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions: a = 1, and g == 0 there
         if (kHasZ) prepass_gate_grad(s_g, s_z, lane);
-#pragma unroll 2
-        for (int c = kTile / 4 - 1; c >= 0; --c) {
-            const float4 d4 = tile_read4(s_dt, lane, c);
-            const float4 g4 = tile_read4(s_g, lane, c);
-            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-            const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-            for (int e = 3; e >= 0; --e) {
-                const int q = 4 * c + e;
-                const float dt = dd[e];
-                const float g = gg[e];
-                sumdt += dt;
-                ragg_step<N>(s_C, q, f2(dt, dt), f2(g, g), A2, mu);
-            }
+#pragma unroll 1
+        for (int c0 = kTile / 4 - 2; c0 >= 0; c0 -= 2) {  // blocks of 8 positions, descending
+            const float *blkC = s_C + 4 * c0 * N;
+            const float4 da = tile_read4(s_dt, lane, c0), db = tile_read4(s_dt, lane, c0 + 1);
+            const float4 ga = tile_read4(s_g, lane, c0), gb = tile_read4(s_g, lane, c0 + 1);
+            const float dd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+            const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            ragg_block<N, 7>(blkC, gg, dd, A2, mu, sumdt);
         }
         __syncwarp();
     }

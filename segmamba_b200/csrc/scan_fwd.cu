@@ -21,30 +21,30 @@ namespace smb {
 //   a = 2^(dt A2) ; h = a h + (dt u) B          [+ y += C h in the main pass]
 // A compile-time subset of the pairs evaluates the decay on the FMA pipe (decay2<M>), the rest on the MUFU.
 // ---------------------------------------------------------------------------------------------
-template <int N, int JN>
-__device__ __forceinline__ void scan_step_agg_chunk(const float *s_B, int q, float2 dt2, float2 du2, const float2 (&A2)[N / 2],
+template <int N, int QL, int JN>
+__device__ __forceinline__ void scan_step_agg_chunk(const float *s_B, float2 dt2, float2 du2, const float2 (&A2)[N / 2],
                                                     float2 (&h)[N / 2]) {
-    const float4 b4 = bc_read4<N>(s_B, q, JN);
+    const float4 b4 = bc_read4_c<N, QL, JN>(s_B);
     const float2 a0 = decay2<2 * JN>(__fmul2_rn(dt2, A2[2 * JN]));
     const float2 a1 = decay2<2 * JN + 1>(__fmul2_rn(dt2, A2[2 * JN + 1]));
     h[2 * JN] = __ffma2_rn(a0, h[2 * JN], __fmul2_rn(du2, f2(b4.x, b4.y)));
     h[2 * JN + 1] = __ffma2_rn(a1, h[2 * JN + 1], __fmul2_rn(du2, f2(b4.z, b4.w)));
 }
-template <int N>
-__device__ __forceinline__ void scan_step_agg(const float *s_B, int q, float2 dt2, float2 du2, const float2 (&A2)[N / 2],
+template <int N, int QL>
+__device__ __forceinline__ void scan_step_agg(const float *s_B, float2 dt2, float2 du2, const float2 (&A2)[N / 2],
                                               float2 (&h)[N / 2]) {
-    scan_step_agg_chunk<N, 0>(s_B, q, dt2, du2, A2, h);
-    scan_step_agg_chunk<N, 1>(s_B, q, dt2, du2, A2, h);
+    scan_step_agg_chunk<N, QL, 0>(s_B, dt2, du2, A2, h);
+    scan_step_agg_chunk<N, QL, 1>(s_B, dt2, du2, A2, h);
     if (N == 16) {
-        scan_step_agg_chunk<N, (N == 16 ? 2 : 0)>(s_B, q, dt2, du2, A2, h);
-        scan_step_agg_chunk<N, (N == 16 ? 3 : 1)>(s_B, q, dt2, du2, A2, h);
+        scan_step_agg_chunk<N, QL, (N == 16 ? 2 : 0)>(s_B, dt2, du2, A2, h);
+        scan_step_agg_chunk<N, QL, (N == 16 ? 3 : 1)>(s_B, dt2, du2, A2, h);
     }
 }
-template <int N, int JN>
-__device__ __forceinline__ void scan_step_main_chunk(const float *s_B, const float *s_C, int q, float2 dt2, float2 du2,
+template <int N, int QL, int JN>
+__device__ __forceinline__ void scan_step_main_chunk(const float *s_B, const float *s_C, float2 dt2, float2 du2,
                                                      const float2 (&A2)[N / 2], float2 (&h)[N / 2], float2 &y) {
-    const float4 b4 = bc_read4<N>(s_B, q, JN);
-    const float4 c4 = bc_read4<N>(s_C, q, JN);
+    const float4 b4 = bc_read4_c<N, QL, JN>(s_B);
+    const float4 c4 = bc_read4_c<N, QL, JN>(s_C);
     const float2 a0 = decay2<2 * JN>(__fmul2_rn(dt2, A2[2 * JN]));
     const float2 a1 = decay2<2 * JN + 1>(__fmul2_rn(dt2, A2[2 * JN + 1]));
     h[2 * JN] = __ffma2_rn(a0, h[2 * JN], __fmul2_rn(du2, f2(b4.x, b4.y)));
@@ -52,18 +52,40 @@ __device__ __forceinline__ void scan_step_main_chunk(const float *s_B, const flo
     y = __ffma2_rn(f2(c4.x, c4.y), h[2 * JN], y);
     y = __ffma2_rn(f2(c4.z, c4.w), h[2 * JN + 1], y);
 }
-template <int N>
-__device__ __forceinline__ float scan_step_main(const float *s_B, const float *s_C, int q, float2 dt2, float2 du2,
+template <int N, int QL>
+__device__ __forceinline__ float scan_step_main(const float *s_B, const float *s_C, float2 dt2, float2 du2,
                                                 const float2 (&A2)[N / 2], float2 (&h)[N / 2]) {
     float2 ya = f2(0.f, 0.f), yb = f2(0.f, 0.f);
-    scan_step_main_chunk<N, 0>(s_B, s_C, q, dt2, du2, A2, h, ya);
-    scan_step_main_chunk<N, 1>(s_B, s_C, q, dt2, du2, A2, h, yb);
+    scan_step_main_chunk<N, QL, 0>(s_B, s_C, dt2, du2, A2, h, ya);
+    scan_step_main_chunk<N, QL, 1>(s_B, s_C, dt2, du2, A2, h, yb);
     if (N == 16) {
-        scan_step_main_chunk<N, (N == 16 ? 2 : 0)>(s_B, s_C, q, dt2, du2, A2, h, ya);
-        scan_step_main_chunk<N, (N == 16 ? 3 : 1)>(s_B, s_C, q, dt2, du2, A2, h, yb);
+        scan_step_main_chunk<N, QL, (N == 16 ? 2 : 0)>(s_B, s_C, dt2, du2, A2, h, ya);
+        scan_step_main_chunk<N, QL, (N == 16 ? 3 : 1)>(s_B, s_C, dt2, du2, A2, h, yb);
     }
     const float2 ys = __fadd2_rn(ya, yb);
     return ys.x + ys.y;
+}
+
+// 8 consecutive positions (compile-time local index QL = 0..7)
+template <int N, int QL>
+__device__ __forceinline__ void agg_block(const float *blkB, const float (&uu)[8], const float (&dd)[8], const float2 (&A2)[N / 2],
+                                          float2 (&h)[N / 2], float &sumdt) {
+    if constexpr (QL < 8) {
+        const float dt = dd[QL], du = dt * uu[QL];
+        sumdt += dt;
+        scan_step_agg<N, QL>(blkB, f2(dt, dt), f2(du, du), A2, h);
+        agg_block<N, QL + 1>(blkB, uu, dd, A2, h, sumdt);
+    }
+}
+template <int N, int QL>
+__device__ __forceinline__ void main_block(const float *blkB, const float *blkC, const float (&uu)[8], const float (&dd)[8], float Dv,
+                                           const float2 (&A2)[N / 2], float2 (&h)[N / 2], float (&yy)[8]) {
+    if constexpr (QL < 8) {
+        const float dt = dd[QL], du = dt * uu[QL];
+        const float ys = scan_step_main<N, QL>(blkB, blkC, f2(dt, dt), f2(du, du), A2, h);
+        yy[QL] = fmaf(Dv, uu[QL], ys);
+        main_block<N, QL + 1>(blkB, blkC, uu, dd, Dv, A2, h, yy);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -121,21 +143,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_agg_kernel(const S
         }
         __syncwarp();
         prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions become scan identities
-#pragma unroll 2
-        for (int c = 0; c < kTile / 4; ++c) {
-            const float4 u4 = tile_read4(s_u, lane, c);
-            const float4 d4 = tile_read4(s_dt, lane, c);
-            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int q = 4 * c + e;
-                const float dt = dd[e];
-                const float du = dt * uu[e];
-                const float2 dt2 = f2(dt, dt), du2 = f2(du, du);
-                sumdt += dt;
-                scan_step_agg<N>(s_B, q, dt2, du2, A2, h);
-            }
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTile / 4; c0 += 2) {      // blocks of 8 positions: all shared offsets are constants
+            const float *blkB = s_B + 4 * c0 * N;
+            const float4 ua = tile_read4(s_u, lane, c0), ub = tile_read4(s_u, lane, c0 + 1);
+            const float4 da = tile_read4(s_dt, lane, c0), db = tile_read4(s_dt, lane, c0 + 1);
+            const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+            const float dd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+            agg_block<N, 0>(blkB, uu, dd, A2, h, sumdt);
         }
         __syncwarp();
     }
@@ -299,29 +314,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
         __syncwarp();
         prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions become scan identities
         if (kHasZ) prepass_silu(s_z, lane);
-#pragma unroll 2
-        for (int c = 0; c < kTile / 4; ++c) {
-            const float4 u4 = tile_read4(s_u, lane, c);
-            const float4 d4 = tile_read4(s_dt, lane, c);
-            float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kHasZ) z4 = tile_read4(s_z, lane, c);
-            const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-            const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-            float yy[4], yz[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int q = 4 * c + e;
-                const float dt = dd[e];
-                const float du = dt * uu[e];
-                const float ys = scan_step_main<N>(s_B, s_C, q, f2(dt, dt), f2(du, du), A2, h);
-                const float y = fmaf(Dv, uu[e], ys);
-                yy[e] = y;
-                yz[e] = y * zz[e];                                  // zz already holds silu(z)
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTile / 4; c0 += 2) {      // blocks of 8 positions: all shared offsets are constants
+            const float *blkB = s_B + 4 * c0 * N, *blkC = s_C + 4 * c0 * N;
+            const float4 ua = tile_read4(s_u, lane, c0), ub = tile_read4(s_u, lane, c0 + 1);
+            const float4 da = tile_read4(s_dt, lane, c0), db = tile_read4(s_dt, lane, c0 + 1);
+            const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+            const float dd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+            float yy[8];
+            main_block<N, 0>(blkB, blkC, uu, dd, Dv, A2, h, yy);
+            if (kHasZ) {
+                const float4 za = tile_read4(s_z, lane, c0), zb = tile_read4(s_z, lane, c0 + 1);   // already silu(z)
+                tile_write4(s_z, lane, c0, make_float4(yy[0] * za.x, yy[1] * za.y, yy[2] * za.z, yy[3] * za.w));
+                tile_write4(s_z, lane, c0 + 1, make_float4(yy[4] * zb.x, yy[5] * zb.y, yy[6] * zb.z, yy[7] * zb.w));
             }
             // in-place: the same lane that consumed (row, c) overwrites it
-            tile_write4(s_u, lane, c, make_float4(yy[0], yy[1], yy[2], yy[3]));
-            if (kHasZ) tile_write4(s_z, lane, c, make_float4(yz[0], yz[1], yz[2], yz[3]));
+            tile_write4(s_u, lane, c0, make_float4(yy[0], yy[1], yy[2], yy[3]));
+            tile_write4(s_u, lane, c0 + 1, make_float4(yy[4], yy[5], yy[6], yy[7]));
         }
         __syncwarp();
         if (out) store_tile<T>(s_u, out, p.out_ds, wi.nrows, j0, p.L, p.reverse, lane);

@@ -5,6 +5,9 @@ import re
 import sys
 
 
+DETAIL = False
+
+
 def main(path, top=30):
     rows = list(csv.reader(open(path)))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -14,7 +17,11 @@ def main(path, top=30):
     for r in rows[hi + 1:]:
         if len(r) <= mv or r[mn] != "gpu__time_duration.sum":
             continue
-        name = re.sub(r"<.*", "", re.sub(r"\(.*", "", r[kn]))[:72]
+        full = r[kn]
+        name = re.sub(r"<.*", "", re.sub(r"\(.*", "", full))[:72]
+        if DETAIL and ("elementwise" in name or name.strip().endswith("at::") or "reduce_kernel" in name or "Kernel2" in name):
+            m = re.search(r"(\w+Functor\w*|\w+_kernel_cuda\w*|\w+Op\b|layer_norm\w*|LayerNorm\w*|cat\w*|CatArray\w*|softmax\w*|nll\w*|\w*[Cc]opy\w*)", full)
+            name = (name + " :: " + (m.group(1) if m else full[len(name):len(name) + 60]))[:110]
         v = float(r[mv].replace(",", ""))
         v = {"ns": v / 1e6, "us": v / 1e3, "usecond": v / 1e3, "ms": v, "msecond": v, "s": v * 1e3, "second": v * 1e3}.get(r[mu], v / 1e6)
         tot[name] += v
@@ -28,4 +35,5 @@ def main(path, top=30):
 
 
 if __name__ == "__main__":
+    DETAIL = len(sys.argv) > 3 and sys.argv[3] == "detail"
     main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30)
