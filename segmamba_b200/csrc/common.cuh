@@ -241,6 +241,19 @@ __device__ __forceinline__ void store_tile(const float *tile, T *base, int64_t r
 //   dt   <- softplus?(delta + bias), forced to 0 for positions >= nvalid (a = 1, b = 0: the scan identity)
 //   gate <- z * sigmoid(z)
 __device__ __forceinline__ void prepass_dt(float *tile, int lane, float bias, bool softplus, int nvalid) {
+    if (nvalid >= kTile) {                               // full tile (warp-uniform): no masking
+#pragma unroll
+        for (int c = 0; c < kTile / 4; ++c) {
+            float4 v = tile_read4(tile, lane, c);
+            float x[4] = {v.x + bias, v.y + bias, v.z + bias, v.w + bias};
+            if (softplus) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = softplus20(x[e]);
+            }
+            tile_write4(tile, lane, c, make_float4(x[0], x[1], x[2], x[3]));
+        }
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < kTile / 4; ++c) {
         float4 v = tile_read4(tile, lane, c);
@@ -304,35 +317,65 @@ template <typename T> __device__ __forceinline__ bool stream_aligned(const T *ba
     return aligned4(base) && (row_stride & 3) == 0 && (!reverse || (L & 3) == 0);
 }
 
+// Per-lane pointers for the fast fills / stores: lane handles chunk c = lane&7 of rows (lane>>3) + 4*it, it = 0..7.
+// lp = address of (row lane>>3, chunk c) for the tile at scan position 0; a tile at j0 is lp +/- j0 and row 4*it is
+// + it*rowstep, so the hot loops contain one 64-bit multiply-add per access and no selects.
+template <typename T> struct LanePtr {
+    const T *lp;
+    int64_t rowstep;
+};
+template <typename T>
+__device__ __forceinline__ LanePtr<T> lane_ptr(const T *base, int64_t row_stride, int L, bool reverse, int lane) {
+    LanePtr<T> r;
+    const int c = lane & 7;
+    r.lp = base + (int64_t)(lane >> 3) * row_stride + (reverse ? (L - 4 - 4 * c) : 4 * c);
+    r.rowstep = 4 * row_stride;
+    return r;
+}
+
 // fill K activation tiles with scan positions [j0, j0+32); REQUIRES j0 + 32 <= L and stream_aligned() for every stream
 template <typename T, int K, int KA>
-__device__ __forceinline__ void fill_tiles_fast(float *const (&tiles)[KA], const T *const (&bases)[KA], const int64_t (&strides)[KA],
-                                                int nrows, int j0, int L, bool reverse, int lane) {
+__device__ __forceinline__ void fill_tiles_fast(float *const (&tiles)[KA], const LanePtr<T> (&lps)[KA], int nrows, int j0,
+                                                bool reverse, int lane) {
     static_assert(K <= KA, "array too small");
     constexpr int H = sizeof(T) == 4 ? 2 : 1;            // fp32: two halves to bound the registers in flight
     constexpr int IT = 8 / H;
+    const int64_t toff = reverse ? -(int64_t)j0 : (int64_t)j0;
+    const int row0 = lane >> 3, c = lane & 7;
 #pragma unroll
     for (int half = 0; half < H; ++half) {
         typename Raw4<T>::type r[K][IT];
 #pragma unroll
         for (int i = 0; i < IT; ++i) {
-            const int unit = (half * IT + i) * 32 + lane;
-            const int row = unit >> 3, c = unit & 7;
-            const int tok = reverse ? L - 4 - (j0 + 4 * c) : j0 + 4 * c;
+            const int it = half * IT + i;
+            const bool ok = row0 + 4 * it < nrows;
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                r[k][i] = row < nrows ? ldraw4<T>(bases[k] + (int64_t)row * strides[k] + tok) : zeroraw4<T>();
+            for (int k = 0; k < K; ++k) r[k][i] = ok ? ldraw4<T>(lps[k].lp + toff + it * lps[k].rowstep) : zeroraw4<T>();
         }
 #pragma unroll
         for (int i = 0; i < IT; ++i) {
-            const int unit = (half * IT + i) * 32 + lane;
-            const int row = unit >> 3, c = unit & 7;
+            const int it = half * IT + i;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 float4 v = cvtraw4<T>(r[k][i]);
                 if (reverse) v = make_float4(v.w, v.z, v.y, v.x);
-                tile_write4(tiles[k], row, c, v);
+                tile_write4(tiles[k], row0 + 4 * it, c, v);
             }
+        }
+    }
+}
+
+// store one tile back (inverse of the fast fill); same requirements
+template <typename T>
+__device__ __forceinline__ void store_tile_fast(const float *tile, T *lp, int64_t rowstep, int nrows, int j0, bool reverse, int lane) {
+    const int64_t toff = reverse ? -(int64_t)j0 : (int64_t)j0;
+    const int row0 = lane >> 3, c = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        if (row0 + 4 * it < nrows) {
+            float4 v = tile_read4(tile, row0 + 4 * it, c);
+            if (reverse) v = make_float4(v.w, v.z, v.y, v.x);
+            store4<T>(lp + toff + it * rowstep, v);
         }
     }
 }

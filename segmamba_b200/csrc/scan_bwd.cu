@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
     const int last_tile = j_begin + ((j_end - j_begin - 1) / kTile) * kTile;
     const bool fast = stream_aligned(dl, p.delta_ds, p.L, p.reverse) && stream_aligned(go, p.dout_ds, p.L, p.reverse) &&
                       (!kHasZ || stream_aligned(z, p.z_ds, p.L, p.reverse));
+    const LanePtr<T> lps[3] = {lane_ptr(dl, p.delta_ds, p.L, p.reverse, lane), lane_ptr(go, p.dout_ds, p.L, p.reverse, lane),
+                               lane_ptr(kHasZ ? z : dl, kHasZ ? p.z_ds : p.delta_ds, p.L, p.reverse, lane)};
     for (int j0 = last_tile; j0 >= j_begin; j0 -= kTile) {
         {
             constexpr int K = kHasZ ? 3 : 2;
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
             const int64_t strides[3] = {p.delta_ds, p.dout_ds, kHasZ ? p.z_ds : p.delta_ds};
             if (fast && j0 + kTile <= p.L) {
                 float *const tiles[3] = {s_dt, s_g, s_z};
-                fill_tiles_fast<T, K, 3>(tiles, bases, strides, wi.nrows, j0, p.L, p.reverse, lane);
+                fill_tiles_fast<T, K, 3>(tiles, lps, wi.nrows, j0, p.reverse, lane);
             } else {
                 fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
                 fill_tile<T>(s_g, go, p.dout_ds, wi.nrows, j0, p.L, p.reverse, lane);

@@ -121,13 +121,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_fwd_agg_kernel(const S
     const int j_begin = wi.seg * p.S;
     const int j_end = min(p.L, j_begin + p.S);
     const bool fast = stream_aligned(u, p.u_ds, p.L, p.reverse) && stream_aligned(dl, p.delta_ds, p.L, p.reverse);
+    const LanePtr<T> lps[2] = {lane_ptr(u, p.u_ds, p.L, p.reverse, lane), lane_ptr(dl, p.delta_ds, p.L, p.reverse, lane)};
     for (int j0 = j_begin; j0 < j_end; j0 += kTile) {
         {
             float *const tiles[2] = {s_u, s_dt};
             const T *const bases[2] = {u, dl};
             const int64_t strides[2] = {p.u_ds, p.delta_ds};
             if (fast && j0 + kTile <= p.L) {
-                fill_tiles_fast<T, 2, 2>(tiles, bases, strides, wi.nrows, j0, p.L, p.reverse, lane);
+                fill_tiles_fast<T, 2, 2>(tiles, lps, wi.nrows, j0, p.reverse, lane);
             } else {
                 fill_tile<T>(s_u, u, p.u_ds, wi.nrows, j0, p.L, p.reverse, lane);
                 fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
@@ -281,6 +282,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
     const int j_end = min(p.L, j_begin + p.S);
     const bool fast = stream_aligned(u, p.u_ds, p.L, p.reverse) && stream_aligned(dl, p.delta_ds, p.L, p.reverse) &&
                       (!kHasZ || stream_aligned(z, p.z_ds, p.L, p.reverse));
+    const LanePtr<T> lps[3] = {lane_ptr(u, p.u_ds, p.L, p.reverse, lane), lane_ptr(dl, p.delta_ds, p.L, p.reverse, lane),
+                               lane_ptr(kHasZ ? z : u, kHasZ ? p.z_ds : p.u_ds, p.L, p.reverse, lane)};
+    const bool fast_out = out ? stream_aligned(out, p.out_ds, p.L, p.reverse) : true;
+    const bool fast_oz = kHasZ ? stream_aligned(out_z, p.out_z_ds, p.L, p.reverse) : true;
+    const LanePtr<T> lpo = lane_ptr(out ? (const T *)out : u, out ? p.out_ds : p.u_ds, p.L, p.reverse, lane);
+    const LanePtr<T> lpz = lane_ptr(kHasZ ? (const T *)out_z : u, kHasZ ? p.out_z_ds : p.u_ds, p.L, p.reverse, lane);
     for (int j0 = j_begin; j0 < j_end; j0 += kTile) {
         if (p.hstates && (j0 % kCkpt) == 0 && active) {
             const int64_t o = (((int64_t)wi.b * (p.nck + 1) + j0 / kCkpt) * N) * p.dim + d;
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
             const T *const bases[3] = {u, dl, kHasZ ? z : u};
             const int64_t strides[3] = {p.u_ds, p.delta_ds, kHasZ ? p.z_ds : p.u_ds};
             if (fast && j0 + kTile <= p.L) {
-                fill_tiles_fast<T, K, 3>(tiles, bases, strides, wi.nrows, j0, p.L, p.reverse, lane);
+                fill_tiles_fast<T, K, 3>(tiles, lps, wi.nrows, j0, p.reverse, lane);
             } else {
                 fill_tile<T>(s_u, u, p.u_ds, wi.nrows, j0, p.L, p.reverse, lane);
                 fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
@@ -333,8 +340,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(con
             tile_write4(s_u, lane, c0 + 1, make_float4(yy[4], yy[5], yy[6], yy[7]));
         }
         __syncwarp();
-        if (out) store_tile<T>(s_u, out, p.out_ds, wi.nrows, j0, p.L, p.reverse, lane);
-        if (kHasZ) store_tile<T>(s_z, out_z, p.out_z_ds, wi.nrows, j0, p.L, p.reverse, lane);
+        const bool full = j0 + kTile <= p.L;
+        if (out) {
+            if (full && fast_out) store_tile_fast<T>(s_u, const_cast<T *>(lpo.lp), lpo.rowstep, wi.nrows, j0, p.reverse, lane);
+            else store_tile<T>(s_u, out, p.out_ds, wi.nrows, j0, p.L, p.reverse, lane);
+        }
+        if (kHasZ) {
+            if (full && fast_oz) store_tile_fast<T>(s_z, const_cast<T *>(lpz.lp), lpz.rowstep, wi.nrows, j0, p.reverse, lane);
+            else store_tile<T>(s_z, out_z, p.out_z_ds, wi.nrows, j0, p.L, p.reverse, lane);
+        }
         __syncwarp();
     }
     if (p.hstates && j_end == p.L && active) {

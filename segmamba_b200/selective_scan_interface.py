@@ -103,6 +103,11 @@ def causal_conv1d_fn(x, weight, bias=None, activation=None):
     return CausalConv1dFn.apply(x, weight, bias, activation)
 
 
+def _as_dbl(t):
+    """(b, d, l) -> (d, b*l) matrix; a view for the channel-major ("HBL") layout the mixer produces, else one copy."""
+    return t.permute(1, 0, 2).reshape(t.shape[1], t.shape[0] * t.shape[2])
+
+
 class MambaInnerFnNoOutProj(torch.autograd.Function):
     """conv1d+SiLU -> x_proj -> dt_proj -> selective scan -> SiLU(z) gate, with recompute in backward
     (ssi.py:155-289, checkpoint_lvl=1).  ``direction`` = 1 walks L in descending order, which equals calling the
@@ -130,22 +135,26 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         conv1d_bias = conv1d_bias.contiguous() if conv1d_bias is not None else None
         conv1d_out = causal_conv1d_cuda.causal_conv1d_fwd_ex(x, conv1d_weight, conv1d_bias, True, direction=direction)
         bsz, d_inner, _ = conv1d_out.shape
-        x_dbl = F.linear(conv1d_out.permute(0, 2, 1).reshape(bsz * L, d_inner), x_proj_weight)          # (bl, R+2N)  :181
-        delta = (delta_proj_weight @ x_dbl[:, :delta_rank].t()).view(d_inner, bsz, L).permute(1, 0, 2)  # HBL   :182
-        Bm = x_dbl[:, delta_rank:delta_rank + d_state].view(bsz, L, d_state).permute(0, 2, 1).unsqueeze(1).contiguous()
-        Cm = x_dbl[:, -d_state:].view(bsz, L, d_state).permute(0, 2, 1).unsqueeze(1).contiguous()
+        # Everything below works on the channel-major (d, b*l) view of the activations ("HBL", ssi.py:178-182), which is
+        # what conv1d_out already is in memory: x_proj / dt_proj become plain GEMMs on that view and B, C are strided
+        # views of their result -- no 'b d l -> (b l) d' transpose copy (ssi.py:181) and no .contiguous() of B / C (:187-207).
+        conv2 = _as_dbl(conv1d_out)                                                     # (d_inner, b*l)
+        x_dblT = x_proj_weight @ conv2                                                  # (R+2N, b*l)   = x_dbl.t()   :181
+        delta = (delta_proj_weight @ x_dblT[:delta_rank]).view(d_inner, bsz, L).permute(1, 0, 2)       # HBL          :182
+        Bm = x_dblT[delta_rank:delta_rank + d_state].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)   # (b,1,N,l) view
+        Cm = x_dblT[-d_state:].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
         D = D.contiguous() if D is not None else None
         _, _, out_z, hst = selective_scan_cuda.fwd_ex(conv1d_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus,
                                                       direction=direction, want_out=False, want_x=False, want_hstates=True)
         ctx.delta_softplus = delta_softplus
         ctx.direction = direction
-        ctx.save_for_backward(xz, conv1d_weight, conv1d_bias, x_dbl, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst)
+        ctx.save_for_backward(xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst)
         return out_z
 
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        (xz, conv1d_weight, conv1d_bias, x_dbl, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst) = ctx.saved_tensors
+        (xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst) = ctx.saved_tensors
         L = xz.shape[-1]
         delta_rank = delta_proj_weight.shape[1]
         d_state = A.shape[-1]
@@ -156,24 +165,24 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         # recompute conv1d_out and delta (ssi.py:238-241)
         conv1d_out = causal_conv1d_cuda.causal_conv1d_fwd_ex(x, conv1d_weight, conv1d_bias, True, direction=direction)
         bsz, d_inner, _ = conv1d_out.shape
-        delta = (delta_proj_weight @ x_dbl[:, :delta_rank].t()).view(d_inner, bsz, L).permute(1, 0, 2)
-        Bm = x_dbl[:, delta_rank:delta_rank + d_state].view(bsz, L, d_state).permute(0, 2, 1).unsqueeze(1).contiguous()
-        Cm = x_dbl[:, -d_state:].view(bsz, L, d_state).permute(0, 2, 1).unsqueeze(1).contiguous()
+        conv2 = _as_dbl(conv1d_out)
+        delta = (delta_proj_weight @ x_dblT[:delta_rank]).view(d_inner, bsz, L).permute(1, 0, 2)
+        Bm = x_dblT[delta_rank:delta_rank + d_state].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
+        Cm = x_dblT[-d_state:].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
         dxz = torch.empty_like(xz)                      # dx and dz are written next to each other (ssi.py:244-245)
         dx, dz = dxz.chunk(2, dim=1)
         dconv1d_out, ddelta, dA, dB, dC, dD, ddelta_bias, dz, _ = selective_scan_cuda.bwd_ex(
             conv1d_out, delta, A, Bm, Cm, D, z, delta_bias, dout, dz, ctx.delta_softplus, False,
             direction=direction, hstates=hst)
-        dx_dbl = torch.empty_like(x_dbl)
-        dx_dbl[:, delta_rank:delta_rank + d_state] = dB.squeeze(1).permute(0, 2, 1).reshape(bsz * L, d_state)   # :255-262
-        dx_dbl[:, -d_state:] = dC.squeeze(1).permute(0, 2, 1).reshape(bsz * L, d_state)                         # :264-271
-        ddelta2 = ddelta.permute(1, 0, 2).reshape(d_inner, bsz * L)                                             # :272
-        ddelta_proj_weight = ddelta2 @ x_dbl[:, :delta_rank]                                                    # :273
-        dx_dbl[:, :delta_rank] = ddelta2.t() @ delta_proj_weight                                                # :274
-        dconv2 = dconv1d_out.permute(1, 0, 2).reshape(d_inner, bsz * L)                                         # :275
-        conv2 = conv1d_out.permute(1, 0, 2).reshape(d_inner, bsz * L)
-        dx_proj_weight = dx_dbl.t() @ conv2.t()                                                                 # :276
-        dconv2 = torch.addmm(dconv2, x_proj_weight.t(), dx_dbl.t())                                             # :277
+        dx_dblT = torch.empty_like(x_dblT)                                                                      # (R+2N, b*l)
+        dx_dblT[delta_rank:delta_rank + d_state].view(d_state, bsz, L).copy_(dB.squeeze(1).permute(1, 0, 2))   # :255-262
+        dx_dblT[-d_state:].view(d_state, bsz, L).copy_(dC.squeeze(1).permute(1, 0, 2))                          # :264-271
+        ddelta2 = _as_dbl(ddelta)                                                                               # :272
+        ddelta_proj_weight = ddelta2 @ x_dblT[:delta_rank].t()                                                  # :273
+        dx_dblT[:delta_rank] = delta_proj_weight.t() @ ddelta2                                                  # :274
+        dconv2 = _as_dbl(dconv1d_out)                                                                           # :275
+        dx_proj_weight = dx_dblT @ conv2.t()                                                                    # :276
+        dconv2 = torch.addmm(dconv2, x_proj_weight.t(), dx_dblT)                                                # :277
         dconv1d_out = dconv2.view(d_inner, bsz, L).permute(1, 0, 2)                                             # :278
         dx, dconv1d_weight, dconv1d_bias = causal_conv1d_cuda.causal_conv1d_bwd_ex(
             x, conv1d_weight, conv1d_bias, dconv1d_out, dx, True, direction=direction)                          # :281-283
