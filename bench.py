@@ -167,7 +167,7 @@ def scan_fwd_bytes(meta):
 
 def scan_bwd_bytes(meta):
     """reads u, delta, z, dout, B, C, saved states; writes du, ddelta, dz and fp32 dB, dC."""
-    batch, dim, L, N, s, has_z, has_hs = meta
+    batch, dim, L, N, s, has_z, has_hs = meta[:7]
     nck = (L + 255) // 256
     streams = 3 + 2 + (2 if has_z else 0)
     return s * batch * L * (streams * dim + 2 * N) + 2 * 4 * batch * N * L + 4 * batch * (nck + 1) * N * dim

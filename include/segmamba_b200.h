@@ -100,6 +100,8 @@ typedef struct smb_scan_bwd_args {
     int32_t dtype;
     int32_t delta_softplus;
     int32_t direction;
+    int32_t low_memory;         /* 0: stash the recomputed states in the workspace (fastest; batch*L*dstate*dim elements);
+                                   1: chunk-parallel recompute in registers (workspace of a few MB) */
     const void *u, *delta, *z /* may be NULL */;
     const float *A, *D, *delta_bias;
     const void *B, *C;
@@ -118,7 +120,8 @@ typedef struct smb_scan_bwd_args {
     size_t workspace_bytes;     /* >= smb_scan_bwd_workspace_bytes(...) */
 } smb_scan_bwd_args;
 
-SMB_API size_t smb_scan_bwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
+SMB_API size_t smb_scan_bwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t dtype,
+                                            int32_t low_memory);
 SMB_API int smb_scan_bwd(const smb_scan_bwd_args *args, void *cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------

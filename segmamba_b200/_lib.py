@@ -35,7 +35,8 @@ class ScanFwdArgs(ctypes.Structure):
 
 class ScanBwdArgs(ctypes.Structure):
     _fields_ = (
-        [(n, _i32) for n in ("batch", "dim", "seqlen", "dstate", "n_groups", "dtype", "delta_softplus", "direction")]
+        [(n, _i32) for n in ("batch", "dim", "seqlen", "dstate", "n_groups", "dtype", "delta_softplus", "direction",
+                             "low_memory")]
         + [(n, _vp) for n in ("u", "delta", "z", "A", "D", "delta_bias", "B", "C", "dout", "hstates", "du", "ddelta",
                               "dz", "out_z", "dA", "dB", "dC", "dD", "ddelta_bias")]
         + [(n, _i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "z_bs", "z_ds", "dout_bs", "dout_ds",
@@ -93,7 +94,7 @@ EXPORTS = {
     "smb_launch_count": (ctypes.c_uint64, []),
     "smb_scan_fwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "smb_scan_fwd": (ctypes.c_int, [ctypes.POINTER(ScanFwdArgs), _vp]),
-    "smb_scan_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "smb_scan_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "smb_scan_bwd": (ctypes.c_int, [ctypes.POINTER(ScanBwdArgs), _vp]),
     "smb_conv1d_fwd": (ctypes.c_int, [ctypes.POINTER(Conv1dArgs), _vp]),
     "smb_conv1d_bwd": (ctypes.c_int, [ctypes.POINTER(Conv1dBwdArgs), _vp]),

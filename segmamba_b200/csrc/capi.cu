@@ -116,10 +116,16 @@ SMB_API int smb_scan_fwd(const smb_scan_fwd_args *a, void *cuda_stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
-SMB_API size_t smb_scan_bwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate) {
+SMB_API size_t smb_scan_bwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t dtype,
+                                            int32_t low_memory) {
     const int nck = (seqlen + smb::kCkpt - 1) / smb::kCkpt;
     const size_t ckf = align_up((size_t)batch * nck * dstate * dim, 64);
-    return sizeof(float) * 6 * ckf;   // Pb, Mloc, Min + (P, H, hin) for the forward-state recompute
+    size_t bytes = sizeof(float) * 6 * ckf;   // Pb, Mloc, Min + (P, H, hin) for the forward-state recompute
+    if (!low_memory) {
+        const size_t lpad = align_up((size_t)seqlen, smb::kTile);
+        bytes += (size_t)batch * lpad * dstate * dim * (dtype == SMB_F32 ? 4 : 2) + 256;
+    }
+    return bytes;
 }
 
 SMB_API int smb_scan_bwd(const smb_scan_bwd_args *a, void *cuda_stream) {
@@ -130,7 +136,7 @@ SMB_API int smb_scan_bwd(const smb_scan_bwd_args *a, void *cuda_stream) {
     if (!a->du || !a->ddelta || !a->dA || !a->dB || !a->dC) return fail(SMB_EINVAL, "smb_scan_bwd: du, ddelta, dA, dB, dC are required");
     if (a->z && !a->dz) return fail(SMB_EINVAL, "smb_scan_bwd: dz is required when z is given");
     if (a->B_ls != 1 || a->C_ls != 1) return fail(SMB_EUNSUPPORTED, "smb_scan_bwd: B and C must have unit stride along L");
-    const size_t need = smb_scan_bwd_workspace_bytes(a->batch, a->dim, a->seqlen, a->dstate);
+    const size_t need = smb_scan_bwd_workspace_bytes(a->batch, a->dim, a->seqlen, a->dstate, a->dtype, a->low_memory);
     if (!a->workspace || a->workspace_bytes < need)
         return fail(SMB_EWORKSPACE, "smb_scan_bwd: workspace of %zu bytes required, got %zu", need, a->workspace_bytes);
     const int N = a->dstate;
@@ -159,6 +165,8 @@ SMB_API int smb_scan_bwd(const smb_scan_bwd_args *a, void *cuda_stream) {
     const size_t ckf = align_up((size_t)a->batch * pl.nck * N * a->dim, 64);
     p.Pb = ws; p.Mloc = ws + ckf; p.Min = ws + 2 * ckf;
     p.P = ws + 3 * ckf; p.H = ws + 4 * ckf; p.hin = ws + 5 * ckf;
+    p.Lpad = (int)align_up((size_t)a->seqlen, smb::kTile);
+    p.stash = a->low_memory ? nullptr : reinterpret_cast<void *>(align_up(reinterpret_cast<size_t>(ws + 6 * ckf), 256));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     cudaError_t e;
     if (a->hstates) {

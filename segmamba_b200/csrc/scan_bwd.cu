@@ -17,6 +17,7 @@
 //     dA  = sum_t lambda dt (h - b)              dB  = sum_d lambda dt u        dC = sum_d g h
 //     ddelta = ddt * sigmoid(delta + bias) (softplus)     dz = dout y sigmoid(z)(1 + z(1 - sigmoid(z)))
 #include "scan_internal.h"
+#include "scan_steps.cuh"
 
 namespace smb {
 
@@ -419,6 +420,342 @@ __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const Sca
     }
 }
 
+// =============================================================================================
+// State-stash backward (default): lane == channel for every pass, no warp scans.
+//   K_F  scan_bwd_stash_kernel   forward recompute from the saved 256-position states, writing every state pair
+//                                h[t, 2m..2m+1] to a workspace stash (bf16x2 for 16-bit I/O, float2 for fp32 I/O)
+//   R1   scan_bwd_ragg_kernel + carry (as above)
+//   K_R  scan_bwd_sweep_kernel   reverse sweep: lambda_t = g_t C_t + mu_{t+1}, mu_t = a_t lambda_t, and every gradient from
+//                                (lambda_t, mu_t, h_t, h_{t-1}); dB / dC are reduced over the warp's 32 channels with a
+//                                shared-memory transpose and leave as one 16-byte vector atomic per (tensor, state) per
+//                                4 positions per warp (red.global.add.v4.f32).
+// dA / ddelta use  lambda_t a_t h_{t-1} = mu_t h_{t-1}  (no h - b cancellation).
+// =============================================================================================
+template <typename T> struct StashT { using type = __nv_bfloat162; };
+template <> struct StashT<float> { using type = float2; };
+__device__ __forceinline__ void stash_store(float2 *p, float2 v) { *p = v; }
+__device__ __forceinline__ void stash_store(__nv_bfloat162 *p, float2 v) { *p = __floats2bfloat162_rn(v.x, v.y); }
+__device__ __forceinline__ float2 stash_cvt(float2 v) { return v; }
+__device__ __forceinline__ float2 stash_cvt(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+template <typename S> __device__ __forceinline__ S stash_zero();
+template <> __device__ __forceinline__ float2 stash_zero<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ __nv_bfloat162 stash_zero<__nv_bfloat162>() { return __floats2bfloat162_rn(0.f, 0.f); }
+
+template <int N, int QL, typename S>
+__device__ __forceinline__ void stash_block(const float *blkB, const float (&uu)[8], const float (&dd)[8], const float2 (&A2)[N / 2],
+                                            float2 (&h)[N / 2], S *sp, int64_t pos_stride, int64_t m_stride, bool active) {
+    if constexpr (QL < 8) {
+        const float dt = dd[QL], du = dt * uu[QL];
+        scan_step_agg<N, QL>(blkB, f2(dt, dt), f2(du, du), A2, h);
+        if (active) {
+#pragma unroll
+            for (int m = 0; m < N / 2; ++m) stash_store(sp + QL * pos_stride + m * m_stride, h[m]);
+        }
+        stash_block<N, QL + 1, S>(blkB, uu, dd, A2, h, sp, pos_stride, m_stride, active);
+    }
+}
+
+template <typename T, int N>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_stash_kernel(const ScanP p) {
+    using S = typename StashT<T>::type;
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kWarpsPerCta + warp;
+    if (w >= p.n_work) return;
+    const WorkItem wi = decode_work(p, w);          // S == kCkpt, n_seg == nck
+    const int d = wi.d0 + lane;
+    const bool active = lane < wi.nrows;
+    float *s_u = smem + warp * (2 * kTile * kTile + kTile * N);
+    float *s_dt = s_u + kTile * kTile;
+    float *s_B = s_dt + kTile * kTile;
+    float2 A2[N / 2], h[N / 2];
+#pragma unroll
+    for (int m = 0; m < N / 2; ++m) {
+        A2[m] = active ? f2(p.A[(int64_t)d * N + 2 * m] * kLog2e, p.A[(int64_t)d * N + 2 * m + 1] * kLog2e) : f2(0.f, 0.f);
+        const int64_t o = (int64_t)wi.b * p.hs_bs + ((int64_t)wi.seg * N + 2 * m) * p.dim + d;
+        h[m] = active ? f2(p.hs[o], p.hs[o + p.dim]) : f2(0.f, 0.f);
+    }
+    const float bias = (active && p.delta_bias) ? p.delta_bias[d] : 0.f;
+    const T *u = reinterpret_cast<const T *>(p.u) + wi.b * p.u_bs + (int64_t)wi.d0 * p.u_ds;
+    const T *dl = reinterpret_cast<const T *>(p.delta) + wi.b * p.delta_bs + (int64_t)wi.d0 * p.delta_ds;
+    const T *Bm = reinterpret_cast<const T *>(p.B) + wi.b * p.B_bs + (int64_t)wi.g * p.B_gs;
+    const int64_t m_stride = p.dim, pos_stride = (int64_t)(N / 2) * p.dim;
+    S *stash = reinterpret_cast<S *>(p.stash) + (int64_t)wi.b * p.Lpad * pos_stride + d;
+
+    const int j_begin = wi.seg * kCkpt;
+    const int j_end = min(p.L, j_begin + kCkpt);
+    const bool fast = stream_aligned(u, p.u_ds, p.L, p.reverse) && stream_aligned(dl, p.delta_ds, p.L, p.reverse);
+    const LanePtr<T> lps[2] = {lane_ptr(u, p.u_ds, p.L, p.reverse, lane), lane_ptr(dl, p.delta_ds, p.L, p.reverse, lane)};
+    for (int j0 = j_begin; j0 < j_end; j0 += kTile) {
+        {
+            float *const tiles[2] = {s_u, s_dt};
+            const T *const bases[2] = {u, dl};
+            const int64_t strides[2] = {p.u_ds, p.delta_ds};
+            if (fast && j0 + kTile <= p.L) {
+                fill_tiles_fast<T, 2, 2>(tiles, lps, wi.nrows, j0, p.reverse, lane);
+            } else {
+                fill_tile<T>(s_u, u, p.u_ds, wi.nrows, j0, p.L, p.reverse, lane);
+                fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
+            }
+            float *const bt[1] = {s_B};
+            const T *const bb[1] = {Bm};
+            const int64_t bns[1] = {p.B_ns}, bls[1] = {p.B_ls};
+            fill_bc_tiles<T, N, 1>(bt, bb, bns, bls, j0, p.L, p.reverse, lane);
+            if (j0 + kTile < j_end) {
+                prefetch_tiles<T, 2, 2>(bases, strides, wi.nrows, j0 + kTile, p.L, p.reverse, lane);
+                prefetch_bc<T, N, 1>(bb, bns, bls, j0 + kTile, p.L, p.reverse, lane);
+            }
+        }
+        __syncwarp();
+        prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);      // masked positions are identities: h is simply repeated
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTile / 4; c0 += 2) {
+            const float *blkB = s_B + 4 * c0 * N;
+            const float4 ua = tile_read4(s_u, lane, c0), ub = tile_read4(s_u, lane, c0 + 1);
+            const float4 da = tile_read4(s_dt, lane, c0), db = tile_read4(s_dt, lane, c0 + 1);
+            const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
+            const float dd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+            stash_block<N, 0, S>(blkB, uu, dd, A2, h, stash + (int64_t)(j0 + 4 * c0) * pos_stride, pos_stride, m_stride, active);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ float sigmoid_of_softplus_inv(float dt) {   // sigmoid(raw) where dt = softplus(raw):  1 - exp(-dt)
+    const float r = 1.f - __expf(-dt);
+    const float s = dt * (1.f - dt * (0.5f - dt * (1.f / 6.f - dt * (1.f / 24.f))));
+    return dt < 0.1f ? s : r;
+}
+
+constexpr int kTrPitch = 36;                    // transpose buffer row pitch (floats): conflict-free STS.128 rows / LDS columns
+
+template <typename T, int N, bool kHasZ>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_bwd_sweep_kernel(const ScanP p) {
+    using S = typename StashT<T>::type;
+    static_assert(N == 16 || N == 8, "dstate");
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kWarpsPerCta + warp;
+    if (w >= p.n_work) return;
+    const WorkItem wi = decode_work(p, w);          // S == kCkpt, n_seg == nck
+    const int d = wi.d0 + lane;
+    const bool active = lane < wi.nrows;
+    constexpr int kWarpFloats = 4 * kTile * kTile + 2 * kTile * N + 32 * kTrPitch;
+    float *s_dt = smem + warp * kWarpFloats;
+    float *s_u = s_dt + kTile * kTile;
+    float *s_g = s_u + kTile * kTile;
+    float *s_z = s_g + kTile * kTile;
+    float *s_B = s_z + kTile * kTile;
+    float *s_C = s_B + kTile * N;
+    float *s_tr = s_C + kTile * N;
+
+    float2 A2[N / 2], mu[N / 2], dA2[N / 2], hcur[N / 2];
+#pragma unroll
+    for (int m = 0; m < N / 2; ++m) {
+        A2[m] = active ? f2(p.A[(int64_t)d * N + 2 * m] * kLog2e, p.A[(int64_t)d * N + 2 * m + 1] * kLog2e) : f2(0.f, 0.f);
+        const int64_t o = (((int64_t)wi.b * p.nck + wi.seg) * N + 2 * m) * p.dim + d;
+        mu[m] = active ? f2(p.Min[o], p.Min[o + p.dim]) : f2(0.f, 0.f);
+        dA2[m] = f2(0.f, 0.f);
+    }
+    const float bias = (active && p.delta_bias) ? p.delta_bias[d] : 0.f;
+    const float Dv = (active && p.D) ? p.D[d] : 0.f;
+    float dDacc = 0.f, dbacc = 0.f;
+
+    const T *u = reinterpret_cast<const T *>(p.u) + wi.b * p.u_bs + (int64_t)wi.d0 * p.u_ds;
+    const T *dl = reinterpret_cast<const T *>(p.delta) + wi.b * p.delta_bs + (int64_t)wi.d0 * p.delta_ds;
+    const T *go = reinterpret_cast<const T *>(p.dout) + wi.b * p.dout_bs + (int64_t)wi.d0 * p.dout_ds;
+    const T *z = kHasZ ? reinterpret_cast<const T *>(p.z) + wi.b * p.z_bs + (int64_t)wi.d0 * p.z_ds : nullptr;
+    const T *Bm = reinterpret_cast<const T *>(p.B) + wi.b * p.B_bs + (int64_t)wi.g * p.B_gs;
+    const T *Cm = reinterpret_cast<const T *>(p.C) + wi.b * p.C_bs + (int64_t)wi.g * p.C_gs;
+    T *du = reinterpret_cast<T *>(p.du) + wi.b * p.du_bs + (int64_t)wi.d0 * p.du_ds;
+    T *dde = reinterpret_cast<T *>(p.ddelta) + wi.b * p.ddelta_bs + (int64_t)wi.d0 * p.ddelta_ds;
+    T *dz = kHasZ ? reinterpret_cast<T *>(p.dz) + wi.b * p.dz_bs + (int64_t)wi.d0 * p.dz_ds : nullptr;
+    T *oz = (kHasZ && p.out_z) ? reinterpret_cast<T *>(p.out_z) + wi.b * p.out_z_bs + (int64_t)wi.d0 * p.out_z_ds : nullptr;
+    const int64_t m_stride = p.dim, pos_stride = (int64_t)(N / 2) * p.dim;
+    const S *stash = reinterpret_cast<const S *>(p.stash) + (int64_t)wi.b * p.Lpad * pos_stride + d;
+    // this lane's slot of the cross-channel reduction: lanes 0..15 -> dB state (lane), lanes 16..31 -> dC state (lane-16)
+    float *dBC = ((lane < 16) ? p.dB : p.dC) + (((int64_t)wi.b * p.G + wi.g) * N + (lane & 15)) * (int64_t)p.L;
+    const bool red_slot = (lane & 15) < N;
+    const bool vec_ok = (p.L & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.dB) | reinterpret_cast<uintptr_t>(p.dC)) & 15) == 0;
+
+    const int j_begin = wi.seg * kCkpt;
+    const int j_end = min(p.L, j_begin + kCkpt);
+    const int last_tile = j_begin + ((j_end - j_begin - 1) / kTile) * kTile;
+    const bool fast = stream_aligned(u, p.u_ds, p.L, p.reverse) && stream_aligned(dl, p.delta_ds, p.L, p.reverse) &&
+                      stream_aligned(go, p.dout_ds, p.L, p.reverse) && (!kHasZ || stream_aligned(z, p.z_ds, p.L, p.reverse));
+    const LanePtr<T> lps[4] = {lane_ptr(dl, p.delta_ds, p.L, p.reverse, lane), lane_ptr(u, p.u_ds, p.L, p.reverse, lane),
+                               lane_ptr(go, p.dout_ds, p.L, p.reverse, lane),
+                               lane_ptr(kHasZ ? z : dl, kHasZ ? p.z_ds : p.delta_ds, p.L, p.reverse, lane)};
+    // state at the last position of the walk
+    {
+        const S *sp = stash + (int64_t)(last_tile + kTile - 1) * pos_stride;
+#pragma unroll
+        for (int m = 0; m < N / 2; ++m) hcur[m] = active ? stash_cvt(sp[m * m_stride]) : f2(0.f, 0.f);
+    }
+    for (int j0 = last_tile; j0 >= j_begin; j0 -= kTile) {
+        {
+            constexpr int K = kHasZ ? 4 : 3;
+            float *const tiles[4] = {s_dt, s_u, s_g, s_z};
+            const T *const bases[4] = {dl, u, go, kHasZ ? z : dl};
+            const int64_t strides[4] = {p.delta_ds, p.u_ds, p.dout_ds, kHasZ ? p.z_ds : p.delta_ds};
+            if (fast && j0 + kTile <= p.L) {
+                fill_tiles_fast<T, K, 4>(tiles, lps, wi.nrows, j0, p.reverse, lane);
+            } else {
+                fill_tile<T>(s_dt, dl, p.delta_ds, wi.nrows, j0, p.L, p.reverse, lane);
+                fill_tile<T>(s_u, u, p.u_ds, wi.nrows, j0, p.L, p.reverse, lane);
+                fill_tile<T>(s_g, go, p.dout_ds, wi.nrows, j0, p.L, p.reverse, lane);
+                if (kHasZ) fill_tile<T>(s_z, z, p.z_ds, wi.nrows, j0, p.L, p.reverse, lane);
+            }
+            float *const bt[2] = {s_B, s_C};
+            const T *const bb[2] = {Bm, Cm};
+            const int64_t bns[2] = {p.B_ns, p.C_ns}, bls[2] = {p.B_ls, p.C_ls};
+            fill_bc_tiles<T, N, 2>(bt, bb, bns, bls, j0, p.L, p.reverse, lane);
+            if (j0 - kTile >= j_begin) {
+                prefetch_tiles<T, K, 4>(bases, strides, wi.nrows, j0 - kTile, p.L, p.reverse, lane);
+                prefetch_bc<T, N, 2>(bb, bns, bls, j0 - kTile, p.L, p.reverse, lane);
+            }
+        }
+        __syncwarp();
+        prepass_dt(s_dt, lane, bias, p.softplus, j_end - j0);
+        if (kHasZ) {
+            // g <- dout * silu(z) ;  z-slot <- dout * d silu(z)/dz  (then dz = slot * y);  if out_z is wanted keep silu(z) instead
+#pragma unroll
+            for (int c = 0; c < kTile / 4; ++c) {
+                const float4 g4 = tile_read4(s_g, lane, c), z4 = tile_read4(s_z, lane, c);
+                const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, zz[4] = {z4.x, z4.y, z4.z, z4.w};
+                float gn[4], zc[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float sg = sigmoidf(zz[e]);
+                    gn[e] = gg[e] * zz[e] * sg;
+                    zc[e] = gg[e] * sg * (1.f + zz[e] * (1.f - sg));
+                }
+                tile_write4(s_g, lane, c, make_float4(gn[0], gn[1], gn[2], gn[3]));
+                tile_write4(s_z, lane, c, make_float4(zc[0], zc[1], zc[2], zc[3]));
+            }
+        }
+#pragma unroll 1
+        for (int c = kTile / 4 - 1; c >= 0; --c) {            // blocks of 4 positions, descending
+            const float4 d4 = tile_read4(s_dt, lane, c), u4 = tile_read4(s_u, lane, c), g4 = tile_read4(s_g, lane, c);
+            float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kHasZ) z4 = tile_read4(s_z, lane, c);
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, uu[4] = {u4.x, u4.y, u4.z, u4.w};
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, zc[4] = {z4.x, z4.y, z4.z, z4.w};
+            float duv[4], ddv[4], dzv[4], red[4];
+            const int q0 = 4 * c;
+            // local position parity decides the constant smem offsets; c even/odd handled by passing the block pointer
+            const float *blkB = s_B + (q0 & ~7) * N, *blkC = s_C + (q0 & ~7) * N;
+#pragma unroll
+            for (int e = 3; e >= 0; --e) {
+                const int pos = j0 + q0 + e;
+                const bool valid = pos < j_end;
+                // h_{t-1}: issue the loads first, consume them at the end of this position
+                S hp[N / 2];
+                {
+                    const S *sp = stash + (int64_t)(pos - 1) * pos_stride;
+#pragma unroll
+                    for (int m = 0; m < N / 2; ++m) hp[m] = (active && pos > 0) ? sp[m * m_stride] : stash_zero<S>();
+                }
+                const float dt = dd[e], uv = uu[e], g = gg[e];
+                const float2 dt2 = f2(dt, dt), g2 = f2(g, g), dtu2 = f2(dt * uv, dt * uv);
+                float2 yacc = f2(0.f, 0.f), slb = f2(0.f, 0.f), saq = f2(0.f, 0.f);
+                float2 vB[N / 2], vC[N / 2];
+                const int ql = (q0 & 4) + e;                     // position inside its block of 8
+#pragma unroll
+                for (int jn = 0; jn < N / 4; ++jn) {
+                    // runtime ql in {0..7}: the swizzle term (ql >> 1) & (N/4 - 1) is cheap; keep bc_read4 generic here
+                    const float4 b4 = *reinterpret_cast<const float4 *>(blkB + ql * N + (((jn ^ ((ql >> 1) & (N / 4 - 1)))) << 2));
+                    const float4 c4 = *reinterpret_cast<const float4 *>(blkC + ql * N + (((jn ^ ((ql >> 1) & (N / 4 - 1)))) << 2));
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int m = 2 * jn + hh;
+                        const float2 Bp = hh ? f2(b4.z, b4.w) : f2(b4.x, b4.y);
+                        const float2 Cp = hh ? f2(c4.z, c4.w) : f2(c4.x, c4.y);
+                        const float2 a = ex2x2_mufu(__fmul2_rn(dt2, A2[m]));
+                        const float2 lam = __ffma2_rn(g2, Cp, mu[m]);
+                        mu[m] = __fmul2_rn(a, lam);
+                        yacc = __ffma2_rn(Cp, hcur[m], yacc);
+                        vC[m] = __fmul2_rn(g2, hcur[m]);
+                        vB[m] = __fmul2_rn(lam, dtu2);
+                        slb = __ffma2_rn(lam, Bp, slb);
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < N / 2; ++m) {
+                    const float2 hpv = stash_cvt(hp[m]);
+                    const float2 qm = __fmul2_rn(mu[m], hpv);                // lambda_t a_t h_{t-1}
+                    dA2[m] = __ffma2_rn(dt2, qm, dA2[m]);
+                    saq = __ffma2_rn(A2[m], qm, saq);
+                    hcur[m] = hpv;
+                }
+                const float y = fmaf(Dv, uv, yacc.x + yacc.y);
+                const float lb = slb.x + slb.y;
+                float ddt = fmaf(uv, lb, kLn2 * (saq.x + saq.y));
+                if (p.softplus) ddt *= sigmoid_of_softplus_inv(dt);
+                ddt = valid ? ddt : 0.f;
+                duv[e] = fmaf(dt, lb, Dv * g);
+                ddv[e] = ddt;
+                dzv[e] = zc[e] * y;
+                dDacc = fmaf(g, uv, dDacc);
+                dbacc += ddt;
+                // ---- reduce vB / vC over the 32 channels of this warp: transpose through shared memory ----
+                float *row = s_tr + lane * kTrPitch;
+#pragma unroll
+                for (int m = 0; m < N / 2; m += 2) {
+                    *reinterpret_cast<float4 *>(row + 2 * m) = make_float4(vB[m].x, vB[m].y, vB[m + 1].x, vB[m + 1].y);
+                    *reinterpret_cast<float4 *>(row + 16 + 2 * m) = make_float4(vC[m].x, vC[m].y, vC[m + 1].x, vC[m + 1].y);
+                }
+                __syncwarp();
+                {
+                    const int col = (lane < 16) ? (lane & 15) : 16 + (lane & 15);
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; r += 4) {
+                        s0 += s_tr[(r + 0) * kTrPitch + col];
+                        s1 += s_tr[(r + 1) * kTrPitch + col];
+                        s2 += s_tr[(r + 2) * kTrPitch + col];
+                        s3 += s_tr[(r + 3) * kTrPitch + col];
+                    }
+                    red[e] = (s0 + s1) + (s2 + s3);
+                }
+                __syncwarp();
+            }
+            // in place: u-slot <- du, dt-slot <- ddelta, z-slot <- dz
+            tile_write4(s_u, lane, c, make_float4(duv[0], duv[1], duv[2], duv[3]));
+            tile_write4(s_dt, lane, c, make_float4(ddv[0], ddv[1], ddv[2], ddv[3]));
+            if (kHasZ) tile_write4(s_z, lane, c, make_float4(dzv[0], dzv[1], dzv[2], dzv[3]));
+            // dB / dC: 4 consecutive positions of this lane's (tensor, state) row
+            if (red_slot) {
+                const int pos0 = j0 + q0;
+                if (pos0 + 3 < p.L && vec_ok) {
+                    float *a = dBC + (p.reverse ? (p.L - 4 - pos0) : pos0);
+                    if (!p.reverse) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(red[0]), "f"(red[1]), "f"(red[2]), "f"(red[3]) : "memory");
+                    else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(red[3]), "f"(red[2]), "f"(red[1]), "f"(red[0]) : "memory");
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (pos0 + e < p.L) atomicAdd(dBC + pos_to_tok(pos0 + e, p.L, p.reverse), red[e]);
+                }
+            }
+        }
+        __syncwarp();
+        store_tile<T>(s_u, du, p.du_ds, wi.nrows, j0, p.L, p.reverse, lane);
+        store_tile<T>(s_dt, dde, p.ddelta_ds, wi.nrows, j0, p.L, p.reverse, lane);
+        if (kHasZ) store_tile<T>(s_z, dz, p.dz_ds, wi.nrows, j0, p.L, p.reverse, lane);
+        __syncwarp();
+    }
+    if (active) {
+#pragma unroll
+        for (int m = 0; m < N / 2; ++m) {
+            atomicAdd(p.dA + (int64_t)d * N + 2 * m, dA2[m].x);
+            atomicAdd(p.dA + (int64_t)d * N + 2 * m + 1, dA2[m].y);
+        }
+        if (p.dD) atomicAdd(p.dD + d, dDacc);
+        if (p.ddelta_bias) atomicAdd(p.ddelta_bias + d, dbacc);
+    }
+    (void)oz;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -432,7 +769,17 @@ static cudaError_t launch_bwd(const ScanP &p, cudaStream_t st) {
     scan_bwd_ragg_kernel<T, N, kHasZ><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
     // R2
     if ((e = carry_launch(p.Pb, p.Mloc, p.Min, nullptr, p.batch, p.nck, N, p.dim, 1, st)) != cudaSuccess) return e;
-    // R3
+    if (p.stash && !(kHasZ && p.out_z)) {
+        // K_F: forward recompute into the stash, then K_R: lane-per-channel reverse sweep
+        const size_t smf = (size_t)kWarpsPerCta * (2 * kTile * kTile + kTile * N) * sizeof(float);
+        SMB_SET_SMEM_ONCE((scan_bwd_stash_kernel<T, N>), smf);
+        scan_bwd_stash_kernel<T, N><<<ctas, kWarpsPerCta * 32, smf, st>>>(p); count_launch();
+        const size_t smr = (size_t)kWarpsPerCta * (4 * kTile * kTile + 2 * kTile * N + 32 * kTrPitch) * sizeof(float);
+        SMB_SET_SMEM_ONCE((scan_bwd_sweep_kernel<T, N, kHasZ>), smr);
+        scan_bwd_sweep_kernel<T, N, kHasZ><<<ctas, kWarpsPerCta * 32, smr, st>>>(p); count_launch();
+        return cudaGetLastError();
+    }
+    // R3 (low-memory path; also used when the caller wants out_z recomputed)
     const size_t sm3 = (size_t)(2 * N + 2 * kBwdWarps) * kRowPad * sizeof(float);
     SMB_SET_SMEM_ONCE((scan_bwd_main_kernel<T, N, kHasZ>), sm3);
     const int octs = ((p.dim_per_group + kBwdWarps - 1) / kBwdWarps) * p.G;

@@ -26,6 +26,8 @@ struct ScanP {
     const float *hs;                               // forward states at every kCkpt-th position: (batch, *, N, dim)
     int64_t hs_bs;                                 // batch stride of hs in floats
     float *Pb, *Mloc, *Min;                        // (batch, nck, N, dim) reverse aggregates / carried adjoints
+    void *stash;                                   // (batch, Lpad, N/2, dim) state pairs (bf16x2 or float2), or nullptr
+    int Lpad;
 };
 
 struct WorkItem {

@@ -107,8 +107,11 @@ def fwd(u, delta, A, B, C, D_, z_, delta_bias_, delta_softplus):
     return [out, x, out_z] if z_ is not None else [out, x]
 
 
+LOW_MEMORY_BWD = False     # True: chunk-parallel recompute backward (small workspace) instead of the state-stash sweep
+
+
 def bwd_ex(u, delta, A, B, C, D_, z_, delta_bias_, dout, dz_=None, delta_softplus=False, recompute_out_z=False, *,
-           direction=0, hstates=None):
+           direction=0, hstates=None, low_memory=None):
     """returns (du, ddelta, dA, dB(fp32), dC(fp32), dD, ddelta_bias, dz | None, out_z | None)."""
     batch, dim, L, N, G, B, C = _validate(u, delta, A, B, C, D_, z_, delta_bias_)
     _lib.require_cuda(dout)
@@ -136,9 +139,11 @@ def bwd_ex(u, delta, A, B, C, D_, z_, delta_bias_, dout, dz_=None, delta_softplu
             if recompute_out_z:
                 out_z = torch.empty_like(z_)
         l = _lib.lib()
-        wsb = l.smb_scan_bwd_workspace_bytes(batch, dim, L, N)
+        low = int(LOW_MEMORY_BWD if low_memory is None else bool(low_memory))
+        wsb = l.smb_scan_bwd_workspace_bytes(batch, dim, L, N, _lib.dtype_code(u.dtype), low)
         ws = _ws(wsb, dev)
         a = _lib.ScanBwdArgs()
+        a.low_memory = low
         a.batch, a.dim, a.seqlen, a.dstate, a.n_groups = batch, dim, L, N, G
         a.dtype = _lib.dtype_code(u.dtype)
         a.delta_softplus = int(bool(delta_softplus))
@@ -163,7 +168,7 @@ def bwd_ex(u, delta, A, B, C, D_, z_, delta_bias_, dout, dz_=None, delta_softplu
         a.C_bs, a.C_gs, a.C_ns, a.C_ls = C.stride(0), C.stride(1), C.stride(2), C.stride(3)
         a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
         sp = _lib.stream_ptr(dev)
-        _lib.call("scan_bwd", (batch, dim, L, N, u.element_size(), has_z, hstates is not None), lambda: l.smb_scan_bwd(ctypes.byref(a), sp), dev)
+        _lib.call("scan_bwd", (batch, dim, L, N, u.element_size(), has_z, hstates is not None, low), lambda: l.smb_scan_bwd(ctypes.byref(a), sp), dev)
     return du, ddelta, dA, dB, dC, dD, dbias, dz, out_z
 
 

@@ -24,10 +24,13 @@ def _run_fwd_bwd(d, has_D=True, has_z=True, has_b=True, softplus=True, direction
     C = d["C"] if d["C"].dim() == 4 else d["C"].unsqueeze(1)
     out, x, out_z, hst = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, D, z, bias, softplus, direction=direction,
                                     want_out=True, want_x=True, want_hstates=True)
+    # g: chunk-parallel recompute path (also returns the recomputed out_z); g2: the default state-stash sweep path
     g = ssc.bwd_ex(d["u"], d["delta"], d["A"], B, C, D, z, bias, d["dout"], None, softplus, True, direction=direction,
-                   hstates=hst if use_hstates else None)
+                   hstates=hst if use_hstates else None, low_memory=True)
+    g2 = ssc.bwd_ex(d["u"], d["delta"], d["A"], B, C, D, z, bias, d["dout"], None, softplus, False, direction=direction,
+                    hstates=hst if use_hstates else None, low_memory=False)
     torch.cuda.synchronize()
-    return out, x, out_z, hst, g
+    return out, x, out_z, hst, g, g2
 
 
 def _oracle_fwd_bwd(d, has_D=True, has_z=True, has_b=True, softplus=True, flip=False):
@@ -49,7 +52,9 @@ def _oracle_fwd_bwd(d, has_D=True, has_z=True, has_b=True, softplus=True, flip=F
 
 
 def _compare(res, ref, dtype, has_z):
-    out, x, out_z, hst, g = res
+    out, x, out_z, hst, g = res[:5]
+    if len(res) > 5:
+        _compare_grads(res[5], ref[4], dtype, has_z, "sweep:")
     y, oz, last, xc, go = ref
     tol, gtol = TOL[dtype], GRAD_TOL[dtype]
     assert_close(out, y, tol, "out")
@@ -58,18 +63,23 @@ def _compare(res, ref, dtype, has_z):
         assert_close(g[8], oz, tol, "recomputed out_z")
     assert_close(x[:, :, -1, 1::2], last, tol, "last_state")
     assert_close(x[..., 1::2], xc[..., 1::2], tol, "x (chunk states)")
+    _compare_grads(g, go, dtype, has_z, "recompute:")
+
+
+def _compare_grads(g, go, dtype, has_z, tag):
+    gtol = GRAD_TOL[dtype]
     du, ddelta, dA, dB, dC, dD, dbias, dz, _ = g
-    assert_close(du, go["du"], gtol, "du")
-    assert_close(ddelta, go["ddelta"], gtol, "ddelta")
-    assert_close(dA, go["dA"], gtol, "dA")
-    assert_close(dB, go["dB"], gtol, "dB")
-    assert_close(dC, go["dC"], gtol, "dC")
+    assert_close(du, go["du"], gtol, tag + "du")
+    assert_close(ddelta, go["ddelta"], gtol, tag + "ddelta")
+    assert_close(dA, go["dA"], gtol, tag + "dA")
+    assert_close(dB, go["dB"], gtol, tag + "dB")
+    assert_close(dC, go["dC"], gtol, tag + "dC")
     if dD is not None:
-        assert_close(dD, go["dD"], gtol, "dD")
+        assert_close(dD, go["dD"], gtol, tag + "dD")
     if dbias is not None:
-        assert_close(dbias, go["ddelta_bias"], gtol, "ddelta_bias")
+        assert_close(dbias, go["ddelta_bias"], gtol, tag + "ddelta_bias")
     if has_z:
-        assert_close(dz, go["dz"], gtol, "dz")
+        assert_close(dz, go["dz"], gtol, tag + "dz")
 
 
 @pytest.mark.parametrize("case", gi.SCAN_CASES, ids=lambda c: c[0])
@@ -86,7 +96,7 @@ def test_scan_vs_golden_and_oracle(case):
     names = ["du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias", "dz"]
     for i, k in enumerate(names):
         if k in gold.files and res[4][i] is not None:
-            got = res[4][i]
+            got = res[5][i]
             if got.dim() == 4 and gold[k].ndim == 3:
                 got = got.squeeze(1)
             assert_close(got, gold[k], 2e-3, k + " vs reference golden")
@@ -134,10 +144,10 @@ def test_scan_strided_hbl_layout():
 
 def test_scan_hstates_equals_recompute():
     d = rand_scan_inputs(11, 2, 96, 3000, 16)
-    a = _run_fwd_bwd(d, use_hstates=True)[4]
-    b = _run_fwd_bwd(d, use_hstates=False)[4]
-    for x, y, n in zip(a[:2], b[:2], ("du", "ddelta")):
-        assert_close(x, y, 1e-5, n)
+    ra, rb = _run_fwd_bwd(d, use_hstates=True), _run_fwd_bwd(d, use_hstates=False)
+    for a, b in ((ra[4], rb[4]), (ra[5], rb[5])):
+        for x, y, n in zip(a[:2], b[:2], ("du", "ddelta")):
+            assert_close(x, y, 1e-5, n)
 
 
 def test_scan_full_size_stage0():
