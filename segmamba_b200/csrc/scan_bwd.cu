@@ -634,18 +634,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_bwd_sweep_kernel(co
                 tile_write4(s_z, lane, c, make_float4(zc[0], zc[1], zc[2], zc[3]));
             }
         }
+        // pull the stash lines of the next (lower) tile into L2 while this one is processed: 8 lines (one per state pair) per
+        // position, lane l covers position l of that tile
+        if (j0 - kTile >= 0 && active) {
+            const S *sp = stash + (int64_t)(j0 - kTile + lane) * pos_stride - lane;      // line start: channel d0
+#pragma unroll
+            for (int m = 0; m < N / 2; ++m) prefetch_l2(sp + m * m_stride);
+        }
 #pragma unroll 1
         for (int c = kTile / 4 - 1; c >= 0; --c) {            // blocks of 4 positions, descending
             const float4 d4 = tile_read4(s_dt, lane, c), u4 = tile_read4(s_u, lane, c), g4 = tile_read4(s_g, lane, c);
             float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (kHasZ) z4 = tile_read4(s_z, lane, c);
-            const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, uu[4] = {u4.x, u4.y, u4.z, u4.w};
-            const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, zc[4] = {z4.x, z4.y, z4.z, z4.w};
-            float duv[4], ddv[4], dzv[4], red[4];
+            float4 duv = make_float4(0.f, 0.f, 0.f, 0.f), ddv = duv, dzv = duv, red = duv;
             const int q0 = 4 * c;
-            // local position parity decides the constant smem offsets; c even/odd handled by passing the block pointer
-            const float *blkB = s_B + (q0 & ~7) * N, *blkC = s_C + (q0 & ~7) * N;
-#pragma unroll
+            const float *blkB = s_B + q0 * N, *blkC = s_C + q0 * N;
+#pragma unroll 1
             for (int e = 3; e >= 0; --e) {
                 const int pos = j0 + q0 + e;
                 const bool valid = pos < j_end;
@@ -656,16 +660,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_bwd_sweep_kernel(co
 #pragma unroll
                     for (int m = 0; m < N / 2; ++m) hp[m] = (active && pos > 0) ? sp[m * m_stride] : stash_zero<S>();
                 }
-                const float dt = dd[e], uv = uu[e], g = gg[e];
+                const float dt = e == 3 ? d4.w : e == 2 ? d4.z : e == 1 ? d4.y : d4.x;
+                const float uv = e == 3 ? u4.w : e == 2 ? u4.z : e == 1 ? u4.y : u4.x;
+                const float g = e == 3 ? g4.w : e == 2 ? g4.z : e == 1 ? g4.y : g4.x;
+                const float zc = e == 3 ? z4.w : e == 2 ? z4.z : e == 1 ? z4.y : z4.x;
                 const float2 dt2 = f2(dt, dt), g2 = f2(g, g), dtu2 = f2(dt * uv, dt * uv);
                 float2 yacc = f2(0.f, 0.f), slb = f2(0.f, 0.f), saq = f2(0.f, 0.f);
                 float2 vB[N / 2], vC[N / 2];
-                const int ql = (q0 & 4) + e;                     // position inside its block of 8
+                const int sw = ((q0 + e) >> 1) & (N / 4 - 1);      // B/C tile swizzle of this position
+                const float *rowB = blkB + e * N, *rowC = blkC + e * N;
 #pragma unroll
                 for (int jn = 0; jn < N / 4; ++jn) {
-                    // runtime ql in {0..7}: the swizzle term (ql >> 1) & (N/4 - 1) is cheap; keep bc_read4 generic here
-                    const float4 b4 = *reinterpret_cast<const float4 *>(blkB + ql * N + (((jn ^ ((ql >> 1) & (N / 4 - 1)))) << 2));
-                    const float4 c4 = *reinterpret_cast<const float4 *>(blkC + ql * N + (((jn ^ ((ql >> 1) & (N / 4 - 1)))) << 2));
+                    const float4 b4 = *reinterpret_cast<const float4 *>(rowB + ((jn ^ sw) << 2));
+                    const float4 c4 = *reinterpret_cast<const float4 *>(rowC + ((jn ^ sw) << 2));
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         const int m = 2 * jn + hh;
@@ -680,6 +687,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_bwd_sweep_kernel(co
                         slb = __ffma2_rn(lam, Bp, slb);
                     }
                 }
+                // ---- reduce vB / vC over the 32 channels of this warp: transpose through shared memory ----
+                float *row = s_tr + lane * kTrPitch;
+#pragma unroll
+                for (int m = 0; m < N / 2; m += 2) {
+                    *reinterpret_cast<float4 *>(row + 2 * m) = make_float4(vB[m].x, vB[m].y, vB[m + 1].x, vB[m + 1].y);
+                    *reinterpret_cast<float4 *>(row + 16 + 2 * m) = make_float4(vC[m].x, vC[m].y, vC[m + 1].x, vC[m + 1].y);
+                }
+                __syncwarp();
 #pragma unroll
                 for (int m = 0; m < N / 2; ++m) {
                     const float2 hpv = stash_cvt(hp[m]);
@@ -693,19 +708,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_bwd_sweep_kernel(co
                 float ddt = fmaf(uv, lb, kLn2 * (saq.x + saq.y));
                 if (p.softplus) ddt *= sigmoid_of_softplus_inv(dt);
                 ddt = valid ? ddt : 0.f;
-                duv[e] = fmaf(dt, lb, Dv * g);
-                ddv[e] = ddt;
-                dzv[e] = zc[e] * y;
+                const float duo = fmaf(dt, lb, Dv * g), dzo = zc * y;
                 dDacc = fmaf(g, uv, dDacc);
                 dbacc += ddt;
-                // ---- reduce vB / vC over the 32 channels of this warp: transpose through shared memory ----
-                float *row = s_tr + lane * kTrPitch;
-#pragma unroll
-                for (int m = 0; m < N / 2; m += 2) {
-                    *reinterpret_cast<float4 *>(row + 2 * m) = make_float4(vB[m].x, vB[m].y, vB[m + 1].x, vB[m + 1].y);
-                    *reinterpret_cast<float4 *>(row + 16 + 2 * m) = make_float4(vC[m].x, vC[m].y, vC[m + 1].x, vC[m + 1].y);
-                }
-                __syncwarp();
+                float rsum;
                 {
                     const int col = (lane < 16) ? (lane & 15) : 16 + (lane & 15);
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -716,25 +722,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_bwd_sweep_kernel(co
                         s2 += s_tr[(r + 2) * kTrPitch + col];
                         s3 += s_tr[(r + 3) * kTrPitch + col];
                     }
-                    red[e] = (s0 + s1) + (s2 + s3);
+                    rsum = (s0 + s1) + (s2 + s3);
                 }
                 __syncwarp();
+                if (e == 3) { duv.w = duo; ddv.w = ddt; dzv.w = dzo; red.w = rsum; }
+                else if (e == 2) { duv.z = duo; ddv.z = ddt; dzv.z = dzo; red.z = rsum; }
+                else if (e == 1) { duv.y = duo; ddv.y = ddt; dzv.y = dzo; red.y = rsum; }
+                else { duv.x = duo; ddv.x = ddt; dzv.x = dzo; red.x = rsum; }
             }
             // in place: u-slot <- du, dt-slot <- ddelta, z-slot <- dz
-            tile_write4(s_u, lane, c, make_float4(duv[0], duv[1], duv[2], duv[3]));
-            tile_write4(s_dt, lane, c, make_float4(ddv[0], ddv[1], ddv[2], ddv[3]));
-            if (kHasZ) tile_write4(s_z, lane, c, make_float4(dzv[0], dzv[1], dzv[2], dzv[3]));
+            tile_write4(s_u, lane, c, duv);
+            tile_write4(s_dt, lane, c, ddv);
+            if (kHasZ) tile_write4(s_z, lane, c, dzv);
             // dB / dC: 4 consecutive positions of this lane's (tensor, state) row
             if (red_slot) {
                 const int pos0 = j0 + q0;
                 if (pos0 + 3 < p.L && vec_ok) {
                     float *a = dBC + (p.reverse ? (p.L - 4 - pos0) : pos0);
-                    if (!p.reverse) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(red[0]), "f"(red[1]), "f"(red[2]), "f"(red[3]) : "memory");
-                    else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(red[3]), "f"(red[2]), "f"(red[1]), "f"(red[0]) : "memory");
+                    if (!p.reverse) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(red.x), "f"(red.y), "f"(red.z), "f"(red.w) : "memory");
+                    else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(red.w), "f"(red.z), "f"(red.y), "f"(red.x) : "memory");
                 } else {
+                    const float rr[4] = {red.x, red.y, red.z, red.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
-                        if (pos0 + e < p.L) atomicAdd(dBC + pos_to_tok(pos0 + e, p.L, p.reverse), red[e]);
+                        if (pos0 + e < p.L) atomicAdd(dBC + pos_to_tok(pos0 + e, p.L, p.reverse), rr[e]);
                 }
             }
         }
