@@ -107,7 +107,8 @@ def fwd(u, delta, A, B, C, D_, z_, delta_bias_, delta_softplus):
     return [out, x, out_z] if z_ is not None else [out, x]
 
 
-LOW_MEMORY_BWD = False     # True: chunk-parallel recompute backward (small workspace) instead of the state-stash sweep
+LOW_MEMORY_BWD = True      # True: chunk-parallel recompute backward (small workspace; currently the faster one on B200);
+                           # False: state-stash forward-recompute + lane-per-channel reverse sweep (workspace = B*L*N*D elements)
 
 
 def bwd_ex(u, delta, A, B, C, D_, z_, delta_bias_, dout, dz_=None, delta_softplus=False, recompute_out_z=False, *,
