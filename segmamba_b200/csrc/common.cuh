@@ -59,9 +59,10 @@ __device__ __forceinline__ float2 ex2x2_poly(float2 x) {
     return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
                        __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
 }
-// which state pairs take the polynomial path (bit m = pair m); tuned on B200, see DESIGN.md section 3.1
+// which state pairs take the polynomial path (bit m = pair m).  Measured on B200 (stage 0, bf16): 0x00 0.658 ms, 0x11 0.689 ms,
+// 0x55 0.793 ms -- the kernels are issue-bound, not MUFU-bound, so the default keeps every decay on the MUFU.
 #ifndef SMB_POLY_MASK
-#define SMB_POLY_MASK 0x11
+#define SMB_POLY_MASK 0x00
 #endif
 template <int M> __device__ __forceinline__ float2 decay2(float2 arg) {
     if ((SMB_POLY_MASK >> M) & 1) return ex2x2_poly(arg);

@@ -173,16 +173,16 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_fwd_kernel(const NormP 
 }
 
 // merge the per-CTA (n, mean, M2) with Chan's parallel formula -> (mean, rstd).
-// Block = 32 channels x 8 partial-groups (coalesced 128-byte reads along the channel axis); grid = (C/32, batch, which).
-__global__ void __launch_bounds__(256) in_finalize_fwd_kernel(const float *__restrict__ partial, float *__restrict__ stats,
+// Block = 32 channels x 32 partial-groups (coalesced 128-byte reads along the channel axis); grid = (C/32, batch, which).
+__global__ void __launch_bounds__(1024) in_finalize_fwd_kernel(const float *__restrict__ partial, float *__restrict__ stats,
                                                               float *__restrict__ stats2, int batch, int C, int n_cta, float eps) {
-    __shared__ float sn[8][32], smean[8][32], sm2[8][32];
+    __shared__ float sn[32][33], smean[32][33], sm2[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx, b = blockIdx.y, which = blockIdx.z;
     float n = 0.f, mean = 0.f, M2 = 0.f;
     if (c < C) {
         const float *pp = partial + (int64_t)which * batch * n_cta * 3 * C + ((int64_t)b * n_cta * 3) * C + c;
-        for (int k = ty; k < n_cta; k += 8) {
+        for (int k = ty; k < n_cta; k += 32) {
             const float nk = pp[(int64_t)k * 3 * C], mk = pp[(int64_t)k * 3 * C + C], qk = pp[(int64_t)k * 3 * C + 2 * C];
             if (nk > 0.f) {
                 const float nt = n + nk, dlt = mk - mean;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) in_finalize_fwd_kernel(const float *__res
     __syncthreads();
     if (ty == 0 && c < C) {
         double dn = 0.0, dmean = 0.0, dM2 = 0.0;
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 32; ++g) {
             const double nk = sn[g][tx], mk = smean[g][tx], qk = sm2[g][tx];
             if (nk <= 0.0) continue;
             const double nt = dn + nk, dlt = mk - dmean;
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(256) in_finalize_fwd_kernel(const float *__res
 // ---------------------------------------------------------------------------------------------
 // forward apply: y = act( (x - mean) rstd  [+ (x2 - mean2) rstd2 | + x2] )
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kNormThreads) in_apply_fwd_kernel(const NormP p) {
+template <typename T, int MODE2>
+__global__ void __launch_bounds__(kNormThreads, 3) in_apply_fwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     const int C = p.channels, CV = C / V;
     const RowMap m = row_map(p, CV);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_fwd_kernel(const NormP 
     const int b = blockIdx.y;
     const int64_t base = (int64_t)b * p.spatial * C;
     const T *x = reinterpret_cast<const T *>(p.x) + base;
-    const T *x2 = p.mode2 ? reinterpret_cast<const T *>(p.x2) + base : nullptr;
+    const T *x2 = MODE2 ? reinterpret_cast<const T *>(p.x2) + base : nullptr;
     T *y = reinterpret_cast<T *>(p.y) + base;
     float mu[V], rs[V], mu2[V], rs2[V];
 #pragma unroll
@@ -232,12 +232,12 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_fwd_kernel(const NormP 
         mu[v] = p.stats[((int64_t)b * C + c) * 2];
         rs[v] = p.stats[((int64_t)b * C + c) * 2 + 1];
         mu2[v] = 0.f; rs2[v] = 1.f;
-        if (p.mode2 == 2) {
+        if (MODE2 == 2) {
             mu2[v] = p.stats2[((int64_t)b * C + c) * 2];
             rs2[v] = p.stats2[((int64_t)b * C + c) * 2 + 1];
         }
     }
-    constexpr int U = 4;
+    constexpr int U = 2;
     for (int64_t row0 = m.row_lo + m.r; row0 < m.row_hi; row0 += (int64_t)U * m.RB) {
         float a[U][V], b2[U][V];
 #pragma unroll
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_fwd_kernel(const NormP 
             const int64_t row = row0 + (int64_t)k * m.RB;
             if (row < m.row_hi) {
                 loadv<T, V>(x + row * C + m.cv * V, a[k]);
-                if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, b2[k]);
+                if (MODE2) loadv<T, V>(x2 + row * C + m.cv * V, b2[k]);
             }
         }
 #pragma unroll
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_fwd_kernel(const NormP 
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     float t = (a[k][v] - mu[v]) * rs[v];
-                    if (p.mode2) t += (b2[k][v] - mu2[v]) * rs2[v];
+                    if (MODE2) t += (b2[k][v] - mu2[v]) * rs2[v];
                     o[v] = act_fwd(t, p.act, p.slope);
                 }
                 storev<T, V>(y + row * C + m.cv * V, o);
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_fwd_kernel(const NormP 
 // backward sums: per-CTA  sum g, sum g*xhat1 (, sum g*xhat2)  with g = dy * act'(pre-activation)
 // partial layout: [batch][cta][3][C]
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kNormThreads) in_stats_bwd_kernel(const NormP p) {
+template <typename T, int MODE2>
+__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? 3 : 2)) in_stats_bwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     extern __shared__ float sm[];
     const int C = p.channels, CV = C / V;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_bwd_kernel(const NormP 
     const int b = blockIdx.y;
     const int64_t base = (int64_t)b * p.spatial * C;
     const T *x = reinterpret_cast<const T *>(p.x) + base;
-    const T *x2 = p.mode2 ? reinterpret_cast<const T *>(p.x2) + base : nullptr;
+    const T *x2 = MODE2 ? reinterpret_cast<const T *>(p.x2) + base : nullptr;
     const T *dy = reinterpret_cast<const T *>(p.dy) + base;
     float mu[V], rs[V], mu2[V], rs2[V], sg[V], sgx[V], sgx2[V];
 #pragma unroll
@@ -287,14 +287,14 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_bwd_kernel(const NormP 
         mu[v] = p.stats[((int64_t)b * C + c) * 2];
         rs[v] = p.stats[((int64_t)b * C + c) * 2 + 1];
         mu2[v] = 0.f; rs2[v] = 1.f;
-        if (p.mode2 == 2) {
+        if (MODE2 == 2) {
             mu2[v] = p.stats2[((int64_t)b * C + c) * 2];
             rs2[v] = p.stats2[((int64_t)b * C + c) * 2 + 1];
         }
         sg[v] = sgx[v] = sgx2[v] = 0.f;
     }
     if (m.active) {
-        constexpr int U = 2;
+        constexpr int U = MODE2 == 0 ? 2 : 1;
         for (int64_t row0 = m.row_lo + m.r; row0 < m.row_hi; row0 += (int64_t)U * m.RB) {
             float a[U][V], a2[U][V], g[U][V];
 #pragma unroll
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_bwd_kernel(const NormP 
                 if (row < m.row_hi) {
                     loadv<T, V>(x + row * C + m.cv * V, a[k]);
                     loadv<T, V>(dy + row * C + m.cv * V, g[k]);
-                    if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, a2[k]);
+                    if (MODE2) loadv<T, V>(x2 + row * C + m.cv * V, a2[k]);
                 }
             }
 #pragma unroll
@@ -314,11 +314,11 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_bwd_kernel(const NormP 
                     for (int v = 0; v < V; ++v) {
                         const float xh = (a[k][v] - mu[v]) * rs[v];
                         float pre = xh, xh2 = 0.f;
-                        if (p.mode2) { xh2 = (a2[k][v] - mu2[v]) * rs2[v]; pre += xh2; }
+                        if (MODE2) { xh2 = (a2[k][v] - mu2[v]) * rs2[v]; pre += xh2; }
                         const float gg = g[k][v] * act_grad(pre, p.act, p.slope);
                         sg[v] += gg;
                         sgx[v] = fmaf(gg, xh, sgx[v]);
-                        if (p.mode2 == 2) sgx2[v] = fmaf(gg, xh2, sgx2[v]);
+                        if (MODE2 == 2) sgx2[v] = fmaf(gg, xh2, sgx2[v]);
                     }
                 }
             }
@@ -344,15 +344,15 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_bwd_kernel(const NormP 
 }
 
 // sums[b][c] = (mean g, mean g*xhat1, mean g*xhat2); same 32 x 8 mapping as the forward finalize
-__global__ void __launch_bounds__(256) in_finalize_bwd_kernel(const float *__restrict__ partial, float *__restrict__ sums, int batch,
+__global__ void __launch_bounds__(1024) in_finalize_bwd_kernel(const float *__restrict__ partial, float *__restrict__ sums, int batch,
                                                               int C, int n_cta, float inv_n) {
-    __shared__ float sa[8][32], sq[8][32], sq2[8][32];
+    __shared__ float sa[32][33], sq[32][33], sq2[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx, b = blockIdx.y;
     float a = 0.f, q = 0.f, q2 = 0.f;
     if (c < C) {
         const float *pp = partial + ((int64_t)b * n_cta * 3) * C + c;
-        for (int k = ty; k < n_cta; k += 8) {
+        for (int k = ty; k < n_cta; k += 32) {
             a += pp[(int64_t)k * 3 * C]; q += pp[(int64_t)k * 3 * C + C]; q2 += pp[(int64_t)k * 3 * C + 2 * C];
         }
     }
@@ -360,15 +360,15 @@ __global__ void __launch_bounds__(256) in_finalize_bwd_kernel(const float *__res
     __syncthreads();
     if (ty == 0 && c < C) {
         double da = 0.0, dq = 0.0, dq2 = 0.0;
-        for (int g = 0; g < 8; ++g) { da += sa[g][tx]; dq += sq[g][tx]; dq2 += sq2[g][tx]; }
+        for (int g = 0; g < 32; ++g) { da += sa[g][tx]; dq += sq[g][tx]; dq2 += sq2[g][tx]; }
         float *o = sums + ((int64_t)b * C + c) * 3;
         o[0] = (float)(da * inv_n); o[1] = (float)(dq * inv_n); o[2] = (float)(dq2 * inv_n);
     }
 }
 
 // backward apply: dx = rstd (g - mean g - xhat mean(g xhat)) ;  dx2 likewise (mode 2) or dx2 = g (mode 1)
-template <typename T>
-__global__ void __launch_bounds__(kNormThreads) in_apply_bwd_kernel(const NormP p) {
+template <typename T, int MODE2>
+__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? 3 : 2)) in_apply_bwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     const int C = p.channels, CV = C / V;
     const RowMap m = row_map(p, CV);
@@ -376,10 +376,10 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_bwd_kernel(const NormP 
     const int b = blockIdx.y;
     const int64_t base = (int64_t)b * p.spatial * C;
     const T *x = reinterpret_cast<const T *>(p.x) + base;
-    const T *x2 = p.mode2 ? reinterpret_cast<const T *>(p.x2) + base : nullptr;
+    const T *x2 = MODE2 ? reinterpret_cast<const T *>(p.x2) + base : nullptr;
     const T *dy = reinterpret_cast<const T *>(p.dy) + base;
     T *dx = reinterpret_cast<T *>(p.dx) + base;
-    T *dx2 = (p.mode2 && p.dx2) ? reinterpret_cast<T *>(p.dx2) + base : nullptr;
+    T *dx2 = (MODE2 && p.dx2) ? reinterpret_cast<T *>(p.dx2) + base : nullptr;
     float mu[V], rs[V], mu2[V], rs2[V], mg[V], mgx[V], mgx2[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_bwd_kernel(const NormP 
         mu[v] = p.stats[((int64_t)b * C + c) * 2];
         rs[v] = p.stats[((int64_t)b * C + c) * 2 + 1];
         mu2[v] = 0.f; rs2[v] = 1.f;
-        if (p.mode2 == 2) {
+        if (MODE2 == 2) {
             mu2[v] = p.stats2[((int64_t)b * C + c) * 2];
             rs2[v] = p.stats2[((int64_t)b * C + c) * 2 + 1];
         }
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_bwd_kernel(const NormP 
         mgx[v] = p.sums[((int64_t)b * C + c) * 3 + 1];
         mgx2[v] = p.sums[((int64_t)b * C + c) * 3 + 2];
     }
-    constexpr int U = 2;
+    constexpr int U = MODE2 == 0 ? 2 : 1;
     for (int64_t row0 = m.row_lo + m.r; row0 < m.row_hi; row0 += (int64_t)U * m.RB) {
         float a[U][V], a2[U][V], g[U][V];
 #pragma unroll
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_bwd_kernel(const NormP 
             if (row < m.row_hi) {
                 loadv<T, V>(x + row * C + m.cv * V, a[k]);
                 loadv<T, V>(dy + row * C + m.cv * V, g[k]);
-                if (p.mode2) loadv<T, V>(x2 + row * C + m.cv * V, a2[k]);
+                if (MODE2) loadv<T, V>(x2 + row * C + m.cv * V, a2[k]);
             }
         }
 #pragma unroll
@@ -416,10 +416,10 @@ __global__ void __launch_bounds__(kNormThreads) in_apply_bwd_kernel(const NormP 
                 for (int v = 0; v < V; ++v) {
                     const float xh = (a[k][v] - mu[v]) * rs[v];
                     float pre = xh, xh2 = 0.f;
-                    if (p.mode2) { xh2 = (a2[k][v] - mu2[v]) * rs2[v]; pre += xh2; }
+                    if (MODE2) { xh2 = (a2[k][v] - mu2[v]) * rs2[v]; pre += xh2; }
                     const float gg = g[k][v] * act_grad(pre, p.act, p.slope);
                     o[v] = rs[v] * (gg - mg[v] - xh * mgx[v]);
-                    o2[v] = p.mode2 == 2 ? rs2[v] * (gg - mg[v] - xh2 * mgx2[v]) : gg;
+                    o2[v] = MODE2 == 2 ? rs2[v] * (gg - mg[v] - xh2 * mgx2[v]) : gg;
                 }
                 storev<T, V>(dx + row * C + m.cv * V, o);
                 if (dx2) storev<T, V>(dx2 + row * C + m.cv * V, o2);
@@ -442,9 +442,11 @@ static cudaError_t norm_fwd_t(NormP p, cudaStream_t st) {
     else in_stats_fwd_kernel<T, false><<<grid, kNormThreads, smem, st>>>(p);
     count_launch();
     dim3 fg((p.channels + 31) / 32, p.batch, two ? 2 : 1);
-    in_finalize_fwd_kernel<<<fg, 256, 0, st>>>(p.partial, p.stats, p.stats2, p.batch, p.channels, p.n_cta, p.eps);
+    in_finalize_fwd_kernel<<<fg, 1024, 0, st>>>(p.partial, p.stats, p.stats2, p.batch, p.channels, p.n_cta, p.eps);
     count_launch();
-    in_apply_fwd_kernel<T><<<grid, kNormThreads, 0, st>>>(p);
+    if (p.mode2 == 0) in_apply_fwd_kernel<T, 0><<<grid, kNormThreads, 0, st>>>(p);
+    else if (p.mode2 == 1) in_apply_fwd_kernel<T, 1><<<grid, kNormThreads, 0, st>>>(p);
+    else in_apply_fwd_kernel<T, 2><<<grid, kNormThreads, 0, st>>>(p);
     count_launch();
     return cudaGetLastError();
 }
@@ -455,12 +457,16 @@ static cudaError_t norm_bwd_t(NormP p, cudaStream_t st) {
     const int CV = p.channels / V, RB = kNormThreads / CV;
     dim3 grid(p.n_cta, p.batch);
     const size_t smem = (size_t)RB * p.channels * 3 * sizeof(float);
-    in_stats_bwd_kernel<T><<<grid, kNormThreads, smem, st>>>(p);
+    if (p.mode2 == 0) in_stats_bwd_kernel<T, 0><<<grid, kNormThreads, smem, st>>>(p);
+    else if (p.mode2 == 1) in_stats_bwd_kernel<T, 1><<<grid, kNormThreads, smem, st>>>(p);
+    else in_stats_bwd_kernel<T, 2><<<grid, kNormThreads, smem, st>>>(p);
     count_launch();
     dim3 fg((p.channels + 31) / 32, p.batch);
-    in_finalize_bwd_kernel<<<fg, 256, 0, st>>>(p.partial, p.sums, p.batch, p.channels, p.n_cta, (float)(1.0 / (double)p.spatial));
+    in_finalize_bwd_kernel<<<fg, 1024, 0, st>>>(p.partial, p.sums, p.batch, p.channels, p.n_cta, (float)(1.0 / (double)p.spatial));
     count_launch();
-    in_apply_bwd_kernel<T><<<grid, kNormThreads, 0, st>>>(p);
+    if (p.mode2 == 0) in_apply_bwd_kernel<T, 0><<<grid, kNormThreads, 0, st>>>(p);
+    else if (p.mode2 == 1) in_apply_bwd_kernel<T, 1><<<grid, kNormThreads, 0, st>>>(p);
+    else in_apply_bwd_kernel<T, 2><<<grid, kNormThreads, 0, st>>>(p);
     count_launch();
     return cudaGetLastError();
 }

@@ -1,6 +1,8 @@
 // Internal parameter block shared by the scan kernels (device + host).
 #pragma once
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace smb {
@@ -52,7 +54,8 @@ __device__ __forceinline__ WorkItem decode_work(const ScanP &p, int w) {
 // Segment length heuristic (host): largest S in {256..2048} that still yields >= 24 warps per SM (two waves at the
 // 12-warp residency the kernels reach) on a 148-SM B200; S divides 2048 so the reference's 2048-position chunk states fall on segment ends.
 inline int plan_segment(int batch, int n_tiles, int L) {
-    const long target = 148L * 24;
+    static const long tune = getenv("SMB_SEG_WARPS_PER_SM") ? atol(getenv("SMB_SEG_WARPS_PER_SM")) : 24;   // tuning knob
+    const long target = 148L * tune;
     int S = 2048;
     while (S > kCkpt && (long)batch * n_tiles * ((L + S - 1) / S) < target) S >>= 1;
     return S;
