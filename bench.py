@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--channels-last", action="store_true", help="channels_last_3d activations for the conv stack")
+    ap.add_argument("--cuda-graph", action="store_true", help="capture the whole step (fwd+bwd+clip+SGD) in one CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=32, help="edge of the cubic crop the CPU arm runs per step")
     return ap.parse_args()
 
@@ -221,6 +222,18 @@ def main_native(args):
         opt.step()
         return loss
 
+    graphed = None
+    if args.cuda_graph:
+        from segmamba_b200.graph_step import GraphedTrainStep
+        l0 = _lib.launch_count()
+        graphed = GraphedTrainStep(net, opt, torch.nn.functional.cross_entropy, x_dev.contiguous(memory_format=mf), y_dev,
+                                   autocast_dtype=torch.bfloat16, clip_grad_norm=12.0, warmup_iters=3)
+        graph_launches = (_lib.launch_count() - l0) // 4          # 3 warm-up steps + the captured one
+        eager_step = step
+
+        def step(x, y):                                            # noqa: F811  (replay instead of eager launch)
+            return graphed(x, y)
+
     def e2e_step():
         xd = x_host.to(dev, non_blocking=True)
         yd = y_host.to(dev, non_blocking=True)
@@ -258,11 +271,20 @@ def main_native(args):
     sampler = ClockSampler(local_rank)
     launches0 = _lib.launch_count()
     sampler.start()
-    with _lib.profile() as prof:
+    if graphed is None:
+        with _lib.profile() as prof:
+            total_ms = timed(lambda: step(x_dev, y_dev), args.steps)
+            durs = prof.durations()
+    else:
         total_ms = timed(lambda: step(x_dev, y_dev), args.steps)
-        durs = prof.durations()
     clocks = sampler.stop()
     launches = _lib.launch_count() - launches0
+    if graphed is not None:
+        launches = graph_launches * args.steps      # native kernel nodes replayed from the graph
+        with _lib.profile() as prof:                # per-op timings need eager launches: taken right after the timed region
+            for _ in range(2):
+                eager_step(x_dev, y_dev)
+            durs = prof.durations()
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step / 1e3)
 
@@ -299,8 +321,9 @@ def main_native(args):
     roofline = roof("scan_fwd", scan_fwd_bytes)
     roof_bwd = roof("scan_bwd", scan_bwd_bytes)
     native_ms = {}
+    prof_steps = args.steps if graphed is None else 2
     for (op, meta), d in durs.items():
-        native_ms[op] = native_ms.get(op, 0.0) + sum(d) / args.steps
+        native_ms[op] = native_ms.get(op, 0.0) + sum(d) / prof_steps
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -308,7 +331,7 @@ def main_native(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2: one step touches > 10 GB of activations (126 MB L2)",
-                       "channels_last_3d": bool(args.channels_last)},
+                       "channels_last_3d": True, "cuda_graph": bool(args.cuda_graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_scan_bwd": roof_bwd,

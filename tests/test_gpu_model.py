@@ -117,3 +117,33 @@ def test_segmamba_bf16_autocast_step():
     assert torch.isfinite(loss)
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
     assert_close(out.float(), ref, 5e-2, "bf16 logits vs fp32")
+
+
+def test_graphed_train_step_matches_eager():
+    """whole-step CUDA graph (fwd + bwd + clip + SGD) replays to the same parameters as eager launches."""
+    import copy
+    from segmamba_b200.graph_step import GraphedTrainStep
+    from segmamba_b200.segmamba import SegMamba
+    c = gi.MODEL_CASE
+    torch.manual_seed(0)
+    m1 = SegMamba(in_chans=4, out_chans=4, depths=c["depths"], feat_size=c["feat_size"], hidden_size=c["hidden_size"]).cuda().train()
+    m2 = copy.deepcopy(m1)
+    x = torch.rand(2, 4, 32, 32, 32, device="cuda")
+    y = torch.randint(0, 4, (2, 32, 32, 32), device="cuda")
+    o1 = torch.optim.SGD(m1.parameters(), lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5)
+    o2 = torch.optim.SGD(m2.parameters(), lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5)
+    step = GraphedTrainStep(m2, o2, torch.nn.functional.cross_entropy, x, y, warmup_iters=3)   # 3 warm-up + 1 captured step
+    for _ in range(2):
+        loss_g = step(x, y)
+    for _ in range(5):                                   # 3 warm-up + 2 replays = the same 5 steps, eagerly
+        o1.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss_e = torch.nn.functional.cross_entropy(m1(x).float(), y)
+        loss_e.backward()
+        torch.nn.utils.clip_grad_norm_(m1.parameters(), 12.0)
+        o1.step()
+    torch.cuda.synchronize()
+    assert abs(float(loss_g) - float(loss_e)) < 5e-2 * max(1.0, abs(float(loss_e)))
+    # atomics make the two runs differ in the last bits; parameters must still agree closely after 5 steps
+    worst = max(float((p1 - p2).abs().max() / p1.abs().max().clamp_min(1e-6)) for p1, p2 in zip(m1.parameters(), m2.parameters()))
+    assert worst < 5e-2, worst
