@@ -174,6 +174,15 @@ def scan_bwd_bytes(meta):
     return s * batch * L * (streams * dim + 2 * N) + 2 * 4 * batch * N * L + 4 * batch * (nck + 1) * N * dim
 
 
+_T0 = time.time()
+
+
+def _log(rank, msg):
+    """progress on stderr (rank 0 only): stdout carries nothing but the final JSON line."""
+    if rank == 0:
+        print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def main_native(args):
     import torch
     import torch.distributed as dist
@@ -187,10 +196,17 @@ def main_native(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        import datetime
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
-        dist.init_process_group(backend="nccl", device_id=dev)
+        # In-switch reduction (NVLS) is a bonus for a 270 MB gradient all-reduce, not a requirement; its
+        # multicast set-up needs fabric-manager support that not every container exposes, so it is opt-in here.
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        _log(rank, "init_process_group(nccl)")
+        dist.init_process_group(backend="nccl", device_id=dev, timeout=datetime.timedelta(minutes=10))
+        dist.barrier()
+        _log(rank, "process group ready")
     _lib.lib()   # fail loudly now if the native library is missing
 
     torch.manual_seed(0)
@@ -259,9 +275,11 @@ def main_native(args):
         return float(ms.item())
 
     W = max(args.warmup, 3)
+    _log(rank, f"model built; {W} warm-up steps")
     for _ in range(W):
         step(x_dev, y_dev)
     barrier()
+    _log(rank, "warm-up done; timing")
     # host-side enqueue time of one step (no synchronisation inside): tells how close the step is to launch-bound
     t0 = time.perf_counter()
     step(x_dev, y_dev)
@@ -288,6 +306,7 @@ def main_native(args):
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step / 1e3)
 
+    _log(rank, f"timed region done: {ms_per_step:.2f} ms/step")
     e2e = None
     if not args.no_e2e:
         e2e_step()
