@@ -174,6 +174,14 @@ def scan_bwd_bytes(meta):
     return s * batch * L * (streams * dim + 2 * N) + 2 * 4 * batch * N * L + 4 * batch * (nck + 1) * N * dim
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per call (all passes of the op) from the committed `ncu --set full` captures,
+# keyed by (op, batch, dim, L, N, element bytes).  Constants from a profiler run, not measured by this script.
+NCU_DRAM_SOURCE = "profiles/r1_ncu_kernels_final_summary.txt (ncu --set full, r9 fwd / r6 bwd captures)"
+NCU_DRAM_BYTES = {
+    ("scan_fwd", 2, 96, 262144, 16, 2): int((218.2 + 16.49 + 348.9 + 95.61) * 1e6),
+    ("scan_bwd", 2, 96, 262144, 16, 2): int((322.0 + 21.53 + 713.4 + 484.6) * 1e6),
+}
+
 _T0 = time.time()
 
 
@@ -198,8 +206,8 @@ def main_native(args):
     if world > 1:
         import datetime
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]               # both levels print a version banner on stdout; keep it to the JSON line
         # In-switch reduction (NVLS) is a bonus for a 270 MB gradient all-reduce, not a requirement; its
         # multicast set-up needs fabric-manager support that not every container exposes, so it is opt-in here.
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
@@ -333,7 +341,9 @@ def main_native(args):
         ms = sum(d) / len(d)
         by = bytes_fn(meta)
         ach = by / (ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+        traffic = NCU_DRAM_BYTES.get((op,) + tuple(meta[:5]))
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                "traffic_source": NCU_DRAM_SOURCE if traffic is not None else None,
                 "kernel": f"smb_{op} (all passes) at batch={meta[0]} dim={meta[1]} L={meta[2]} N={meta[3]} elt={meta[4]}B",
                 "algorithmic_bytes": by, "avg_ms": ms, "launches_timed": len(d), "peak_source": peak_src}
 
