@@ -100,8 +100,10 @@ typedef struct smb_scan_bwd_args {
     int32_t dtype;
     int32_t delta_softplus;
     int32_t direction;
-    int32_t low_memory;         /* 0: stash the recomputed states in the workspace (fastest; batch*L*dstate*dim elements);
-                                   1: chunk-parallel recompute in registers (workspace of a few MB) */
+    int32_t low_memory;         /* 1: chunk-parallel recompute in registers, workspace of a few MB (the shim's default and
+                                      the faster path as measured on B200);
+                                   0: stash every recomputed state in the workspace (batch*L*dstate*dim elements) and
+                                      sweep backwards once -- fewer instructions per update, more HBM traffic */
     const void *u, *delta, *z /* may be NULL */;
     const float *A, *D, *delta_bias;
     const void *B, *C;
