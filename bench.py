@@ -211,6 +211,9 @@ def main_native(args):
         # In-switch reduction (NVLS) is a bonus for a 270 MB gradient all-reduce, not a requirement; its
         # multicast set-up needs fabric-manager support that not every container exposes, so it is opt-in here.
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        if rank == 0:                                 # if a collective stalls, say where (stderr; stdout stays the JSON line)
+            import faulthandler
+            faulthandler.dump_traceback_later(300, repeat=True, file=sys.stderr)
         _log(rank, "init_process_group(nccl)")
         dist.init_process_group(backend="nccl", device_id=dev, timeout=datetime.timedelta(minutes=10))
         dist.barrier()
@@ -372,6 +375,9 @@ def main_native(args):
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:
+        if rank == 0:
+            import faulthandler
+            faulthandler.cancel_dump_traceback_later()
         dist.destroy_process_group()
 
 
