@@ -41,11 +41,12 @@ def main():
         if os.path.exists(target):
             print("build_ref:", target, "exists")
             continue
-        bdir = os.path.join("/tmp", "smb_ref_build", name)
+        bdir = os.path.join(OUT, "_build", name)           # scratch inside the git-ignored output directory, removed below
         os.makedirs(bdir, exist_ok=True)
         load(name=name, sources=[os.path.join(d, f) for f in files], extra_include_paths=[d], extra_cflags=["-O3", "-std=c++17"],
              extra_cuda_cflags=nvcc, build_directory=bdir, verbose=False, is_python_module=False)
         shutil.copy(os.path.join(bdir, name + ".so"), target)
+        shutil.rmtree(os.path.join(OUT, "_build"), ignore_errors=True)
         print("build_ref: built", target)
     return 0
 

@@ -42,7 +42,7 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 ex2x2_mufu(float2 x) { return make_float2(ex2(x.x), ex2(x.y)); }
 // 2^x for x <= 0 on the FMA pipe (Cody-Waite split + degree-6 polynomial, rel. error ~2e-7, same class as MUFU.EX2):
-// the scan kernels are MUFU-bound, so a fraction of the decays is evaluated here to balance the two pipes.
+// lets a fraction of the decays move off the MUFU pipe (see SMB_POLY_MASK below for what that measured).
 __device__ __forceinline__ float2 ex2x2_poly(float2 x) {
     x.x = fmaxf(x.x, -126.f);
     x.y = fmaxf(x.y, -126.f);
