@@ -274,11 +274,80 @@ def gen_sw():
     print("sw", res["starts_brats"].shape, res["blend_small"].shape)
 
 
+def load_reference_poly_lr():
+    """the reference's PolyLRScheduler class (light_training/utils/lr_scheduler.py:22-38).  It passes a third positional
+    argument (`verbose`) to `_LRScheduler.__init__`, which torch >= 2.7 no longer accepts, so the base class is wrapped to
+    swallow it; everything else (the initial `step()` issued by the base constructor included) is the reference's code."""
+    import importlib.util
+    import torch.optim.lr_scheduler as tls
+    base = tls._LRScheduler
+
+    class _Compat(base):
+        def __init__(self, optimizer, last_epoch=-1, verbose=False):
+            super().__init__(optimizer, last_epoch)
+
+    tls._LRScheduler = _Compat
+    try:
+        spec = importlib.util.spec_from_file_location("ref_lr_scheduler", os.path.join(REF, "light_training", "utils", "lr_scheduler.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        tls._LRScheduler = base
+    return mod.PolyLRScheduler
+
+
+def train_toy_model():
+    """stand-in network for the host-side training-loop fixtures (fixed seed, CPU, fp32)."""
+    torch.manual_seed(7)
+    return torch.nn.Sequential(torch.nn.Conv3d(2, 6, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv3d(6, 3, 1))
+
+
+def gen_train():
+    """PolyLRScheduler trajectory and six iterations of the reference's inner training loop (trainer.py:444-477: grads to None,
+    forward, CE loss, backward, clip_grad_norm_ 12, SGD-nesterov step, scheduler step) on a toy network, CPU fp32."""
+    Poly = load_reference_poly_lr()
+    res = {}
+    p = [torch.nn.Parameter(torch.zeros(1))]
+    opt = torch.optim.SGD(p, lr=1e-2)
+    sch = Poly(opt, initial_lr=1e-2, max_steps=10)
+    lrs = [opt.param_groups[0]["lr"]]
+    for _ in range(9):
+        opt.step()
+        sch.step()
+        lrs.append(opt.param_groups[0]["lr"])
+    res["poly_lrs"] = np.array(lrs, dtype=np.float64)
+
+    model = train_toy_model()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)   # 3_train.py:51-52
+    sch = Poly(opt, initial_lr=1e-2, max_steps=20)
+    ce = torch.nn.CrossEntropyLoss()
+    rs = np.random.RandomState(70)
+    xs = torch.from_numpy(rs.standard_normal((6, 2, 2, 8, 8, 8)).astype(np.float32))
+    ys = torch.from_numpy(rs.randint(0, 3, (6, 2, 8, 8, 8)).astype(np.int64))
+    losses = []
+    for i in range(6):
+        for prm in model.parameters():
+            prm.grad = None
+        loss = ce(model(xs[i]), ys[i])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 12)
+        opt.step()
+        sch.step()
+        losses.append(float(loss))
+    res["train_x"], res["train_y"] = xs.numpy(), ys.numpy()
+    res["train_losses"] = np.array(losses, dtype=np.float64)
+    res["train_final_lr"] = np.array(opt.param_groups[0]["lr"], dtype=np.float64)
+    for k, v in model.state_dict().items():
+        res["train_param_" + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "train_loop.npz"), **res)
+    print("train", res["poly_lrs"], losses)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="scan,conv,inner,mamba,model,sw")
+    ap.add_argument("--only", default="scan,conv,inner,mamba,model,sw,train")
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     for part in args.only.split(","):
-        {"scan": gen_scan, "conv": gen_conv, "inner": gen_inner, "mamba": gen_mamba, "model": gen_model, "sw": gen_sw}[part]()
+        {"scan": gen_scan, "conv": gen_conv, "inner": gen_inner, "mamba": gen_mamba, "model": gen_model, "sw": gen_sw, "train": gen_train}[part]()

@@ -130,3 +130,10 @@ def reference_like_init(keys, shapes):
         else:
             sd[k] = torch.zeros(s)
     return sd
+
+
+def train_toy_model():
+    """stand-in network of the training-loop fixture (oracle/gen_golden.py: train_toy_model)."""
+    import torch
+    torch.manual_seed(7)
+    return torch.nn.Sequential(torch.nn.Conv3d(2, 6, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv3d(6, 3, 1))
