@@ -33,11 +33,15 @@ constexpr float kLn2 = 0.6931471805599453f;
 // math.  The decay uses the MUFU ex2 path with A pre-scaled by log2(e), as the reference kernel
 // does (selective_scan_fwd_kernel.cuh:169-171,216).
 // ---------------------------------------------------------------------------------------------
+#ifdef SMB_EMU   // host build for tools/simt_emu (functional tests without a GPU): no PTX
+__device__ __forceinline__ float ex2(float x) { return exp2f(x); }
+#else
 __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#endif
 // ---- packed fp32x2 (Blackwell FFMA2 / FMUL2 / FADD2: two lanes of fp32 per issue slot) ----
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 ex2x2_mufu(float2 x) { return make_float2(ex2(x.x), ex2(x.y)); }
@@ -311,7 +315,18 @@ template <> __device__ __forceinline__ float4 cvtraw4<__nv_bfloat16>(uint2 r) { 
     return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
                        __uint_as_float(r.y & 0xffff0000u));
 }
+#ifdef SMB_EMU
+__device__ __forceinline__ void prefetch_l2(const void *) {}
+__device__ __forceinline__ void red_add_v4(float *a, float x, float y, float z, float w) {
+    atomicAdd(a, x); atomicAdd(a + 1, y); atomicAdd(a + 2, z); atomicAdd(a + 3, w);
+}
+#else
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one 16-byte vector reduction: 4 consecutive fp32 accumulators, address aligned to 16 bytes
+__device__ __forceinline__ void red_add_v4(float *a, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+#endif
 
 // true when 4-element vector accesses of a (rows, L) operand are aligned for every full tile of this walk
 template <typename T> __device__ __forceinline__ bool stream_aligned(const T *base, int64_t row_stride, int L, bool reverse) {

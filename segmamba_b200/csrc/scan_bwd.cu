@@ -739,8 +739,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) scan_bwd_sweep_kernel(co
                 const int pos0 = j0 + q0;
                 if (pos0 + 3 < p.L && vec_ok) {
                     float *a = dBC + (p.reverse ? (p.L - 4 - pos0) : pos0);
-                    if (!p.reverse) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(red.x), "f"(red.y), "f"(red.z), "f"(red.w) : "memory");
-                    else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(red.w), "f"(red.z), "f"(red.y), "f"(red.x) : "memory");
+                    if (!p.reverse) red_add_v4(a, red.x, red.y, red.z, red.w);
+                    else red_add_v4(a, red.w, red.z, red.y, red.x);
                 } else {
                     const float rr[4] = {red.x, red.y, red.z, red.w};
 #pragma unroll

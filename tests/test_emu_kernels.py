@@ -1,0 +1,237 @@
+"""The native CUDA kernels, run WITHOUT a GPU: csrc/*.cu compiled for the host by tools/simt_emu (one fiber per CUDA thread,
+SIMT barrier / shuffle semantics, shared memory poisoned with NaN on block entry) and driven through the unmodified Python
+shims and the C ABI.  Parity against the oracle and the reference's golden vectors at small sizes.
+
+This is a functional check of what the kernel code computes (indexing, tails, strides, barriers, reductions) that the CPU-only
+suite can run; it is not a product path (tests/emu.py) and says nothing about performance.  The `-m gpu` suite runs the
+same comparisons on the real device at full sizes.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import emu
+import golden_inputs as gi
+import test_gpu_scan as tg
+from util import GRAD_TOL, TOL, assert_close, rand_scan_inputs
+
+
+@pytest.fixture(autouse=True)
+def _emulated():
+    with emu.emulated():
+        emu.emu_lib().smb_emu_set_reverse(0)
+        yield
+
+
+def _oracle():
+    from oracle import oracle as orc
+    return orc
+
+
+# ---------------------------------------------------------------------------------------------------------- selective scan
+@pytest.mark.parametrize("case", gi.SCAN_CASES, ids=lambda c: c[0])
+def test_emu_scan_vs_golden_and_oracle(case):
+    name, seed, batch, dim, L, N, G, tl, has_D, has_z, has_b, sp = case
+    d = gi.scan_inputs(seed, batch, dim, L, N, G, tl)
+    res = tg._run_fwd_bwd(d, has_D, has_z, has_b, sp)
+    ref = tg._oracle_fwd_bwd(d, has_D, has_z, has_b, sp)
+    tg._compare(res, ref, torch.float32, has_z)
+    gold = gi.load("scan_" + name)
+    assert_close(res[2] if has_z else res[0], gold["out"], 1e-3, "out vs reference golden")
+    assert_close(res[1][:, :, -1, 1::2], gold["last_state"], 1e-3, "last_state vs reference golden")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16], ids=["f32", "f16", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 40, 700, 16, 1), (1, 33, 31, 16, 1), (2, 48, 600, 8, 2), (1, 64, 2300, 16, 1)],
+                         ids=lambda s: "b%d_d%d_L%d_n%d_g%d" % s)
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_emu_scan_random_vs_oracle(dtype, shape, direction):
+    batch, dim, L, N, G = shape
+    d = rand_scan_inputs(100 + L, batch, dim, L, N, G, dtype, device="cpu")
+    res = tg._run_fwd_bwd(d, direction=direction, use_hstates=(L % 2 == 0))
+    ref = tg._oracle_fwd_bwd(d, flip=bool(direction))
+    tg._compare(res, ref, dtype, True)
+
+
+def test_emu_scan_descending_lane_order():
+    """same kernels with the threads of every block resumed in descending order: a cross-lane shared-memory dependency that
+    lacks a barrier produces a different (wrong) result in one of the two orders."""
+    emu.emu_lib().smb_emu_set_reverse(1)
+    d = rand_scan_inputs(9, 2, 40, 900, 16, 1, torch.float32, device="cpu")
+    for direction in (0, 1):
+        res = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)
+        ref = tg._oracle_fwd_bwd(d, flip=bool(direction))
+        tg._compare(res, ref, torch.float32, True)
+
+
+def test_emu_scan_strided_hbl_layout():
+    batch, dim, L, N = 2, 64, 500, 16
+    d = rand_scan_inputs(7, batch, dim, L, N, device="cpu")
+    hbl = lambda t: t.permute(1, 0, 2).contiguous().permute(1, 0, 2)
+    d2 = dict(d)
+    for k in ("u", "delta", "z", "dout"):
+        d2[k] = hbl(d[k])
+        assert d2[k].stride() == (L, batch * L, 1)
+    tg._compare(tg._run_fwd_bwd(d2), tg._oracle_fwd_bwd(d), torch.float32, True)
+
+
+# ------------------------------------------------------------------------------------------------- conv1d and seq permute
+@pytest.mark.parametrize("case", gi.CONV_CASES, ids=lambda c: c[0])
+def test_emu_conv_vs_golden(case):
+    from segmamba_b200 import causal_conv1d_cuda as cc
+    name, seed, batch, dim, L, width, has_b, silu = case
+    d = gi.conv_inputs(seed, batch, dim, L, width)
+    b = d["bias"] if has_b else None
+    out = cc.causal_conv1d_fwd(d["x"], d["weight"], b, silu)
+    dx, dw, db = cc.causal_conv1d_bwd(d["x"], d["weight"], b, d["dout"], None, silu)
+    gold = gi.load("conv_" + name)
+    assert_close(out, gold["out"], 1e-3, "out vs golden")
+    assert_close(dx, gold["dx"], 1e-3, "dx vs golden")
+    assert_close(dw, gold["dweight"], 1e-3, "dweight vs golden")
+    if has_b:
+        assert_close(db, gold["dbias"], 1e-3, "dbias vs golden")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 40, 1300, 4), (1, 33, 1031, 3), (2, 8, 7, 2)], ids=lambda s: "b%d_d%d_L%d_w%d" % s)
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_emu_conv_random_vs_oracle(dtype, shape, direction):
+    from segmamba_b200 import causal_conv1d_cuda as cc
+    orc = _oracle()
+    batch, dim, L, width = shape
+    d = gi.conv_inputs(200 + L, batch, dim, L, width)
+    x, dout, w, b = d["x"].to(dtype), d["dout"].to(dtype), d["weight"], d["bias"]
+    xz = torch.empty(2 * dim, batch, L, dtype=dtype).permute(1, 0, 2)      # channel-major views, dx in place (ssi.py:244-245,281)
+    xz[:, :dim] = x
+    xv = xz[:, :dim]
+    dxz = torch.zeros_like(xz)
+    out = cc.causal_conv1d_fwd_ex(xv, w, b, True, direction=direction)
+    dx, dw, db = cc.causal_conv1d_bwd_ex(xv, w, b, dout, dxz[:, :dim], True, direction=direction)
+    f = (lambda t: t.flip(-1)) if direction else (lambda t: t)
+    o = f(orc.causal_conv1d_fwd_raw(f(x.float()), w, b, True))
+    odx, odw, odb = orc.causal_conv1d_bwd_raw(f(x.float()), w, b, f(dout.float()), True)
+    assert_close(out, o, TOL[dtype], "out")
+    assert_close(dxz[:, :dim], f(odx), GRAD_TOL[dtype], "dx (in place)")
+    assert float(dxz[:, dim:].abs().max()) == 0.0
+    assert_close(dw, odw, GRAD_TOL[dtype], "dweight")
+    assert_close(db, odb, GRAD_TOL[dtype], "dbias")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_emu_seq_permute(dtype):
+    from segmamba_b200 import causal_conv1d_cuda as cc
+    for (b, d, L, ns) in [(2, 12, 1024, 32), (1, 10, 512, 8), (2, 6, 96, 16)]:
+        x = torch.randn(b, d, L).to(dtype)
+        ref = torch.stack(x.chunk(ns, dim=-1), dim=-1).flatten(-2)
+        got = cc.seq_permute(x, ns)
+        assert torch.equal(got, ref)
+        assert torch.equal(cc.seq_permute(got, ns, inverse=True), x)
+        hbl = x.permute(1, 0, 2).contiguous().permute(1, 0, 2)
+        assert torch.equal(cc.seq_permute(hbl, ns), ref)
+
+
+# ----------------------------------------------------------------------------------------------------- fused instance norm
+def _in_ref(x, add, add_norm, act, slope):
+    v = F.instance_norm(x.float(), eps=1e-5)
+    if add is not None:
+        v = v + (F.instance_norm(add.float(), eps=1e-5) if add_norm else add.float())
+    if act == "relu":
+        v = F.relu(v)
+    elif act == "leaky_relu":
+        v = F.leaky_relu(v, slope)
+    return v
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 48, 8, 8, 8), (1, 96, 9, 7, 5), (2, 768, 2, 2, 2), (1, 32, 20, 13, 11)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("mode,act", [("plain", None), ("plain", "relu"), ("add", "leaky_relu"), ("addnorm", "leaky_relu")])
+def test_emu_fused_instance_norm(dtype, shape, mode, act):
+    from segmamba_b200.instance_norm import fused_instance_norm
+    torch.manual_seed(sum(shape))
+    x = (torch.randn(shape) * 2.0 + 0.7).to(dtype).contiguous(memory_format=torch.channels_last_3d).requires_grad_()
+    add = (torch.randn(shape) * 0.5 - 0.3).to(dtype).requires_grad_() if mode != "plain" else None
+    dy = torch.randn(shape).to(dtype)
+    y = fused_instance_norm(x, act, 0.01, add=add, add_norm=(mode == "addnorm"))
+    assert y.is_contiguous(memory_format=torch.channels_last_3d) and y.dtype == dtype
+    gx = torch.autograd.grad(y, [x] + ([add] if add is not None else []), dy)
+    xr = x.detach().clone().requires_grad_()
+    ar = add.detach().clone().requires_grad_() if add is not None else None
+    yr = _in_ref(xr, ar, mode == "addnorm", act, 0.01)
+    gr = torch.autograd.grad(yr, [xr] + ([ar] if ar is not None else []), dy.float())
+    assert_close(y, yr, 1e-4 if dtype == torch.float32 else 1e-2, "y")
+    for a, b, n in zip(gx, gr, ("dx", "dadd")):
+        assert_close(a, b, 2e-4 if dtype == torch.float32 else 3e-2, n)
+
+
+def test_emu_fused_instance_norm_large_mean():
+    from segmamba_b200.instance_norm import fused_instance_norm
+    x = (torch.randn(1, 16, 16, 16, 16) * 0.01 + 50.0).contiguous(memory_format=torch.channels_last_3d)
+    assert_close(fused_instance_norm(x), F.instance_norm(x.double(), eps=1e-5).float(), 2e-3, "y (mean 50, std 0.01)")
+
+
+# --------------------------------------------------------------------------------------- fused inner op, mixer, full module
+@pytest.mark.parametrize("case", gi.INNER_CASES, ids=lambda c: c[0])
+def test_emu_inner_vs_reference_golden(case):
+    from segmamba_b200.selective_scan_interface import mamba_inner_fn_no_out_proj
+    name, seed, batch, d_model, L = case
+    d = gi.inner_inputs(seed, batch, d_model, L)
+    gold = gi.load("inner_" + name)
+    keys = ["xz", "conv1d_weight", "conv1d_bias", "x_proj_weight", "delta_proj_weight", "A", "D", "delta_bias"]
+    lv = {k: d[k].clone().requires_grad_() for k in keys}
+    out = mamba_inner_fn_no_out_proj(lv["xz"], lv["conv1d_weight"], lv["conv1d_bias"], lv["x_proj_weight"],
+                                     lv["delta_proj_weight"], lv["A"], None, None, lv["D"], delta_bias=lv["delta_bias"],
+                                     delta_softplus=True)
+    assert_close(out, gold["out"], 1e-3, "out")
+    grads = torch.autograd.grad(out, [lv[k] for k in keys], d["dout"])
+    for k, g in zip(keys, grads):
+        assert_close(g, gold["d" + k], 2e-3, "d" + k)
+
+
+@pytest.mark.parametrize("case", gi.MAMBA_CASES, ids=lambda c: c[0])
+def test_emu_mamba_v3_vs_reference_golden(case):
+    from segmamba_b200.mamba_simple import Mamba
+    name, seed, batch, d_model, L, ns = case
+    gold = gi.load("mamba_" + name)
+    m = Mamba(d_model=d_model, d_state=16, d_conv=4, expand=2, bimamba_type="v3", nslices=ns)
+    m.load_state_dict({k[len("param."):]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("param.")}, strict=True)
+    r = np.random.RandomState(seed + 1000)
+    x = torch.from_numpy(r.standard_normal((batch, L, d_model)).astype(np.float32)).requires_grad_()
+    dout = torch.from_numpy(r.standard_normal((batch, L, d_model)).astype(np.float32))
+    out = m(x)
+    assert_close(out, gold["out"], 1e-3, "out")
+    names = [n for n, _ in m.named_parameters()]
+    grads = torch.autograd.grad(out, [x] + [p for _, p in m.named_parameters()], dout)
+    assert_close(grads[0], gold["dx"], 2e-3, "dx")
+    for n, g in zip(names, grads[1:]):
+        assert_close(g, gold["grad." + n], 3e-3, "grad." + n)
+
+
+def test_emu_segmamba_vs_reference_golden():
+    """full module forward + backward on the tiny fixture: every native kernel (scan, conv1d, permute, instance norm) in its
+    place inside the model, dense convs / GEMMs by CPU PyTorch, against the reference SegMamba's golden outputs."""
+    from segmamba_b200.segmamba import SegMamba
+    c = gi.MODEL_CASE
+    gold = gi.load("model_" + c["name"])
+    m = SegMamba(in_chans=c["in_chans"], out_chans=c["out_chans"], depths=c["depths"], feat_size=c["feat_size"],
+                 hidden_size=c["hidden_size"])
+    keys = [str(k) for k in gold["state_dict_keys"]]
+    shapes = [tuple(int(s) for s in str(x).split(",")) if str(x) else () for x in gold["state_dict_shapes"]]
+    m.load_state_dict(gi.randomize_state_dict(gi.reference_like_init(keys, shapes), c["seed"]), strict=True)
+    m.train()
+    x = gi.model_input(c["seed"] + 1, (c["batch"], c["in_chans"], c["spatial"], c["spatial"], c["spatial"]))
+    out = m(x)
+    assert_close(out, gold["out"], 1e-3, "logits")
+    r = np.random.RandomState(c["seed"] + 2)
+    dout = torch.from_numpy(r.standard_normal(tuple(out.shape)).astype(np.float32)) / out.numel() ** 0.5
+    names = [n for n, _ in m.named_parameters()]
+    grads = torch.autograd.grad(out, [p for _, p in m.named_parameters()], dout)
+    norms = np.array([float(g.double().norm()) for g in grads])
+    ref_norms = gold["grad_norms"]
+    floor = 1e-4 * float(ref_norms.max())
+    bad = [(n, a, b) for n, a, b in zip(names, norms, ref_norms) if abs(a - b) > 5e-3 * b + floor]
+    assert not bad, f"grad norm mismatch: {bad[:5]}"
+    for n, g, rn in zip(names, grads, ref_norms):
+        if "grad." + n in gold.files and rn > 10 * floor:
+            assert_close(g, gold["grad." + n], 2e-2, "grad." + n)

@@ -1,0 +1,265 @@
+// simt_emu.cpp -- scheduler of the CPU SIMT emulator (see simt_emu.h).  TEST INFRASTRUCTURE ONLY.
+#include "simt_emu.h"
+
+#include <memory>
+#include <mutex>
+
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
+
+// ---- context switch.  swapcontext() makes a sigprocmask system call per switch; on x86-64 a callee-saved-register switch
+// in a few instructions is used instead (fibers never touch the signal mask, MXCSR or the x87 control word). ----
+#if defined(__x86_64__)
+#define SMB_EMU_FAST_SWITCH 1
+extern "C" void smb_emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl smb_emu_switch
+.type smb_emu_switch,@function
+smb_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size smb_emu_switch,.-smb_emu_switch
+)");
+#endif
+
+namespace emu {
+
+thread_local Block *g_block = nullptr;
+
+static size_t stack_bytes() {
+    static const size_t v = (getenv("SMB_EMU_STACK_KB") ? (size_t)atol(getenv("SMB_EMU_STACK_KB")) : 256) * 1024;
+    return v;
+}
+static std::atomic<int> g_reverse{-1};
+static bool reverse_order() {
+    int v = g_reverse.load();
+    if (v < 0) {
+        v = getenv("SMB_EMU_REVERSE") && atoi(getenv("SMB_EMU_REVERSE")) != 0;
+        g_reverse.store(v);
+    }
+    return v != 0;
+}
+static int worker_count() {
+    static const int v = getenv("SMB_EMU_THREADS") ? atoi(getenv("SMB_EMU_THREADS")) : (int)std::thread::hardware_concurrency();
+    return v > 0 ? v : 1;
+}
+
+[[noreturn]] void die(const char *msg) {
+    fprintf(stderr, "simt_emu: %s (block %u,%u,%u thread %u,%u,%u)\n", msg, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x,
+            threadIdx.y, threadIdx.z);
+    fflush(stderr);
+    abort();
+}
+
+void yield_wait(State st, unsigned mask) {
+    Block *b = g_block;
+    Fiber &f = b->fibers[b->cur];
+    f.st = st;
+    f.wait_mask = mask;
+#ifdef SMB_EMU_FAST_SWITCH
+    smb_emu_switch(&f.sp, b->sched_sp);
+#else
+    swapcontext(&f.ctx, &b->sched);
+#endif
+}
+
+uint64_t *warp_exchange(unsigned mask, uint64_t mine) {
+    Block *b = g_block;
+    Fiber &f = b->fibers[b->cur];
+    const int tid = linear_tid();
+    const int warp = tid >> 5, lane = tid & 31;
+    if (!((mask >> lane) & 1)) die("a lane calls a warp collective with a mask that does not name it");
+    const int parity = f.seq & 1;
+    uint64_t *slots = &b->xchg[(size_t)(warp * 2 + parity) * 32];
+    slots[lane] = mine;
+    f.seq++;
+    yield_wait(WAIT_WARP, mask);
+    f.last_part = b->part[(size_t)(warp * 2 + parity)];
+    return slots;
+}
+
+bool lane_live_and_in_mask(int src_lane, unsigned mask) {
+    Block *b = g_block;
+    if (src_lane < 0 || src_lane > 31) return false;
+    if (!((mask >> src_lane) & 1)) return false;
+    return (b->fibers[b->cur].last_part >> src_lane) & 1;     // took part in the same collective (it may have exited since)
+}
+
+static void fiber_entry() {
+    Block *b = g_block;
+    (*b->body)();
+    Fiber &f = b->fibers[b->cur];
+    f.st = DONE;
+#ifdef SMB_EMU_FAST_SWITCH
+    smb_emu_switch(&f.sp, b->sched_sp);     // never resumed
+    abort();
+#endif
+    // ucontext: returning resumes uc_link (the scheduler)
+}
+
+static void run_block(Block &b, unsigned char *stacks) {
+    const int n = b.nthreads;
+    const size_t ss = stack_bytes();
+    for (int i = 0; i < n; ++i) {
+        Fiber &f = b.fibers[i];
+        f.st = READY;
+        f.seq = 0;
+        f.wait_mask = 0;
+        const unsigned x = i % blockDim.x, y = (i / blockDim.x) % blockDim.y, z = i / (blockDim.x * blockDim.y);
+        f.tid = make_uint3(x, y, z);
+#ifdef SMB_EMU_FAST_SWITCH
+        // initial frame: six zeroed callee-saved registers, the entry point as return address, one pad word so that the
+        // entry function sees the stack alignment of a normal call (rsp = 16n + 8)
+        uintptr_t top = ((uintptr_t)(stacks + (size_t)(i + 1) * ss)) & ~(uintptr_t)15;
+        void **sp = reinterpret_cast<void **>(top);
+        *--sp = nullptr;
+        *--sp = reinterpret_cast<void *>(&fiber_entry);
+        for (int r = 0; r < 6; ++r) *--sp = nullptr;
+        f.sp = sp;
+#else
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = stacks + (size_t)i * ss;
+        f.ctx.uc_stack.ss_size = ss;
+        f.ctx.uc_link = &b.sched;
+        makecontext(&f.ctx, fiber_entry, 0);
+#endif
+    }
+    const bool rev = reverse_order();
+    const int nwarps = (n + 31) / 32;
+    for (;;) {
+        bool ran = false;
+        for (int k = 0; k < n; ++k) {
+            const int i = rev ? n - 1 - k : k;
+            Fiber &f = b.fibers[i];
+            if (f.st != READY) continue;
+            b.cur = i;
+            threadIdx = f.tid;
+#ifdef SMB_EMU_FAST_SWITCH
+            smb_emu_switch(&b.sched_sp, f.sp);
+#else
+            swapcontext(&b.sched, &f.ctx);
+#endif
+            ran = true;
+        }
+        int live = 0, at_block = 0;
+        for (int i = 0; i < n; ++i) {
+            live += b.fibers[i].st != DONE;
+            at_block += b.fibers[i].st == WAIT_BLOCK;
+        }
+        if (live == 0) return;
+        bool released = false;
+        if (at_block == live) {
+            for (int i = 0; i < n; ++i)
+                if (b.fibers[i].st == WAIT_BLOCK) b.fibers[i].st = READY;
+            released = true;
+        }
+        for (int w = 0; w < nwarps; ++w) {
+            const int lo = w * 32, hi = std::min(n, lo + 32);
+            for (int i = lo; i < hi; ++i) {
+                Fiber &f = b.fibers[i];
+                if (f.st != WAIT_WARP) continue;
+                bool ok = true;
+                for (int j = lo; j < hi && ok; ++j) {
+                    if (!((f.wait_mask >> (j - lo)) & 1)) continue;
+                    const Fiber &g = b.fibers[j];
+                    if (g.st == DONE) continue;                       // exited lanes are not waited for (as on hardware)
+                    ok = g.st == WAIT_WARP && g.seq == f.seq && g.wait_mask == f.wait_mask;
+                }
+                if (!ok) continue;
+                // release every lane of this collective together
+                unsigned part = 0;
+                const int parity = (f.seq - 1) & 1;
+                for (int j = lo; j < hi; ++j) {
+                    Fiber &g = b.fibers[j];
+                    if (((f.wait_mask >> (j - lo)) & 1) && g.st == WAIT_WARP && g.seq == f.seq) {
+                        g.st = READY;
+                        part |= 1u << (j - lo);
+                    }
+                }
+                b.part[(size_t)(w * 2 + parity)] = part;
+                released = true;
+            }
+        }
+        if (!ran && !released) {
+            fprintf(stderr, "simt_emu: deadlock in block (%u,%u,%u): no runnable thread.  states:", blockIdx.x, blockIdx.y, blockIdx.z);
+            for (int i = 0; i < n; ++i) fprintf(stderr, " %d:%d/%d", i, (int)b.fibers[i].st, b.fibers[i].seq);
+            fprintf(stderr, "\n");
+            abort();
+        }
+    }
+}
+
+void run_grid(const std::function<void()> &body, dim3 grid, dim3 block, size_t smem_bytes) {
+    const long nblocks = (long)grid.x * grid.y * grid.z;
+    const int nthreads = (int)(block.x * block.y * block.z);
+    if (nblocks <= 0 || nthreads <= 0 || nthreads > 1024) {
+        fprintf(stderr, "simt_emu: bad launch configuration grid=(%u,%u,%u) block=(%u,%u,%u)\n", grid.x, grid.y, grid.z, block.x, block.y,
+                block.z);
+        abort();
+    }
+    if (smem_bytes > 227 * 1024) {
+        fprintf(stderr, "simt_emu: %zu bytes of dynamic shared memory exceed the 227 KB of an sm_100 CTA\n", smem_bytes);
+        abort();
+    }
+    std::atomic<long> next{0};
+    const int nw = (int)std::min<long>(worker_count(), nblocks);
+    auto worker = [&]() {
+        Block b;
+        b.nthreads = nthreads;
+        b.fibers.resize(nthreads);
+        b.xchg.assign((size_t)((nthreads + 31) / 32) * 2 * 32, 0);
+        b.part.assign((size_t)((nthreads + 31) / 32) * 2, 0);
+        b.body = &body;
+        std::unique_ptr<unsigned char[]> stacks(new unsigned char[(size_t)nthreads * stack_bytes()]);   // untouched pages cost nothing
+        std::vector<unsigned char> smem(smem_bytes + 256);
+        b.dyn_smem = (unsigned char *)(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127);
+        g_block = &b;
+        gridDim = grid;
+        blockDim = block;
+        for (;;) {
+            const long id = next.fetch_add(1);
+            if (id >= nblocks) break;
+            blockIdx = make_uint3((unsigned)(id % grid.x), (unsigned)((id / grid.x) % grid.y), (unsigned)(id / ((long)grid.x * grid.y)));
+            memset(b.dyn_smem, 0xff, smem_bytes);                       // NaN poison: shared memory is not zero on entry
+            run_block(b, stacks.get());
+        }
+        g_block = nullptr;
+    };
+    if (nw == 1) {
+        worker();
+    } else {
+        std::vector<std::thread> ts;
+        for (int i = 0; i < nw; ++i) ts.emplace_back(worker);
+        for (auto &t : ts) t.join();
+    }
+}
+
+}  // namespace emu
+
+// resume order of the threads of a block: 0 ascending, 1 descending (tests run both to expose missing barriers)
+extern "C" __attribute__((visibility("default"))) void smb_emu_set_reverse(int on) { emu::g_reverse.store(on ? 1 : 0); }
+
+// ---- the slice of the CUDA runtime the sources call: "device" memory is host memory, streams are synchronous ----
+extern "C" {
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaPeekAtLastError(void) { return cudaSuccess; }
+const char *cudaGetErrorString(cudaError_t) { return "simt_emu: no CUDA runtime"; }
+cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaFuncSetAttribute(const void *, cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+}
