@@ -14,6 +14,7 @@
  *   smb_conv1d_bwd    causal_conv1d_cuda.causal_conv1d_bwd   causal-conv1d/csrc/causal_conv1d.cpp:191-268
  *   smb_instnorm_*    nn.InstanceNorm3d + activation + residual chains of GSC / UnetResBlock,
  *                     model_segmamba/segmamba.py:111-130, monai/networks/blocks/dynunet_block.py:98-111
+ *   smb_layernorm_*   nn.LayerNorm(dim) of MambaLayer, model_segmamba/segmamba.py:54,70
  *   smb_seq_permute   the flip / inter-slice re-orderings of Mamba.forward (v3),
  *                     mamba/mamba_ssm/modules/mamba_simple.py:230-261
  *
@@ -224,6 +225,38 @@ typedef struct smb_instnorm_bwd_args {
 SMB_API size_t smb_instnorm_workspace_bytes(int32_t batch, int32_t channels, int64_t spatial, int32_t dtype);
 SMB_API int smb_instnorm_fwd(const smb_instnorm_args *args, void *cuda_stream);
 SMB_API int smb_instnorm_bwd(const smb_instnorm_bwd_args *args, void *cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused LayerNorm over the last axis of a contiguous (rows, channels) token matrix:
+ *     y = (x - mean) * rsqrt(var + eps) * gamma + beta        (biased variance, fp32 arithmetic)
+ * Replaces nn.LayerNorm(dim) in MambaLayer.forward (model_segmamba/segmamba.py:54,70); x / y / dy / dx in the
+ * activation dtype, gamma / beta / dgamma / dbeta fp32.  channels must be a multiple of 16 / sizeof(element), at most
+ * 128 vectors of 16 bytes and at most 768; x, y, dy, dx must be 16-byte aligned.  The backward recomputes the row
+ * statistics (nothing is saved by the forward) and ACCUMULATES into dgamma / dbeta, which the caller zero-initialises.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct smb_layernorm_args {
+    int64_t rows;
+    int32_t channels;
+    int32_t dtype;
+    float eps;
+    const void *x;
+    const float *gamma, *beta;  /* beta may be NULL */
+    void *y;
+} smb_layernorm_args;
+
+typedef struct smb_layernorm_bwd_args {
+    int64_t rows;
+    int32_t channels;
+    int32_t dtype;
+    float eps;
+    const void *x, *dy;
+    const float *gamma;
+    void *dx;
+    float *dgamma, *dbeta;      /* dbeta may be NULL */
+} smb_layernorm_bwd_args;
+
+SMB_API int smb_layernorm_fwd(const smb_layernorm_args *args, void *cuda_stream);
+SMB_API int smb_layernorm_bwd(const smb_layernorm_bwd_args *args, void *cuda_stream);
 
 #ifdef __cplusplus
 }

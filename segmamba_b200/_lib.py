@@ -87,6 +87,16 @@ class InstNormBwdArgs(ctypes.Structure):
     )
 
 
+class LayerNormArgs(ctypes.Structure):
+    _fields_ = ([("rows", _i64), ("channels", _i32), ("dtype", _i32), ("eps", ctypes.c_float)]
+                + [(n, _vp) for n in ("x", "gamma", "beta", "y")])
+
+
+class LayerNormBwdArgs(ctypes.Structure):
+    _fields_ = ([("rows", _i64), ("channels", _i32), ("dtype", _i32), ("eps", ctypes.c_float)]
+                + [(n, _vp) for n in ("x", "dy", "gamma", "dx", "dgamma", "dbeta")])
+
+
 # every symbol include/segmamba_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = {
     "smb_version": (ctypes.c_int, []),
@@ -102,6 +112,8 @@ EXPORTS = {
     "smb_instnorm_workspace_bytes": (_sz, [_i32, _i32, _i64, _i32]),
     "smb_instnorm_fwd": (ctypes.c_int, [ctypes.POINTER(InstNormArgs), _vp]),
     "smb_instnorm_bwd": (ctypes.c_int, [ctypes.POINTER(InstNormBwdArgs), _vp]),
+    "smb_layernorm_fwd": (ctypes.c_int, [ctypes.POINTER(LayerNormArgs), _vp]),
+    "smb_layernorm_bwd": (ctypes.c_int, [ctypes.POINTER(LayerNormBwdArgs), _vp]),
 }
 
 _lib = None

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 
 #include "../../include/segmamba_b200.h"
@@ -310,6 +311,45 @@ SMB_API int smb_instnorm_bwd(const smb_instnorm_bwd_args *a, void *cuda_stream) 
     p.stats = const_cast<float *>(a->stats); p.stats2 = const_cast<float *>(a->stats2);
     cudaError_t e = smb::instnorm_dispatch(p, a->dtype, true, (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return cuda_fail(e, "smb_instnorm_bwd");
+    return SMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int ln_common(int64_t rows, int channels, int dtype, const void *p0, const void *p1, const void *p2, const char *who) {
+    if (rows <= 0 || channels <= 0) return fail(SMB_EINVAL, "%s: rows and channels must be positive", who);
+    if (dtype < SMB_F32 || dtype > SMB_BF16) return fail(SMB_EINVAL, "%s: bad dtype %d", who, dtype);
+    const int V = dtype == SMB_F32 ? 4 : 8;
+    if (channels % V != 0) return fail(SMB_EUNSUPPORTED, "%s: channels %d not a multiple of %d", who, channels, V);
+    if (channels / V > 128 || channels > 768) return fail(SMB_EUNSUPPORTED, "%s: channels %d too large", who, channels);
+    if (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15) return fail(SMB_EINVAL, "%s: activation pointers must be 16-byte aligned", who);
+    return SMB_OK;
+}
+
+SMB_API int smb_layernorm_fwd(const smb_layernorm_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_layernorm_fwd: null args");
+    if (!a->x || !a->y || !a->gamma) return fail(SMB_EINVAL, "smb_layernorm_fwd: x, y, gamma are required");
+    int rc = ln_common(a->rows, a->channels, a->dtype, a->x, a->y, nullptr, "smb_layernorm_fwd");
+    if (rc) return rc;
+    smb::LnP p;
+    memset(&p, 0, sizeof(p));
+    p.rows = a->rows; p.C = a->channels; p.eps = a->eps; p.x = a->x; p.gamma = a->gamma; p.beta = a->beta; p.y = a->y;
+    cudaError_t e = smb::layernorm_dispatch(p, a->dtype, false, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_layernorm_fwd");
+    return SMB_OK;
+}
+
+SMB_API int smb_layernorm_bwd(const smb_layernorm_bwd_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_layernorm_bwd: null args");
+    if (!a->x || !a->dy || !a->dx || !a->gamma || !a->dgamma)
+        return fail(SMB_EINVAL, "smb_layernorm_bwd: x, dy, dx, gamma, dgamma are required");
+    int rc = ln_common(a->rows, a->channels, a->dtype, a->x, a->dy, a->dx, "smb_layernorm_bwd");
+    if (rc) return rc;
+    smb::LnP p;
+    memset(&p, 0, sizeof(p));
+    p.rows = a->rows; p.C = a->channels; p.eps = a->eps; p.x = a->x; p.dy = a->dy; p.gamma = a->gamma; p.dx = a->dx;
+    p.dgamma = a->dgamma; p.dbeta = a->dbeta;
+    cudaError_t e = smb::layernorm_dispatch(p, a->dtype, true, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_layernorm_bwd");
     return SMB_OK;
 }
 

@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import layer_norm
 from .instance_norm import fused_instance_norm
 from .mamba_simple import Mamba
 
@@ -119,7 +120,11 @@ class MambaLayer(nn.Module):
         if x.is_contiguous(memory_format=_CL):
             # channels-last storage IS the (B, L, C) token matrix: both reshapes are views
             x_flat = x.permute(0, 2, 3, 4, 1).reshape(B, n_tokens, C)
-            x_mamba = self.mamba(self.norm(x_flat))
+            if layer_norm.ENABLED and layer_norm.supported(x_flat, C):
+                x_norm = layer_norm.fused_layer_norm(x_flat, self.norm.weight, self.norm.bias, self.norm.eps)
+            else:
+                x_norm = self.norm(x_flat)
+            x_mamba = self.mamba(x_norm)
             out = x_mamba.reshape(B, *img_dims, C).permute(0, 4, 1, 2, 3)
             return out + x
         x_flat = x.reshape(B, C, n_tokens).transpose(-1, -2)

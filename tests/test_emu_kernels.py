@@ -235,3 +235,59 @@ def test_emu_segmamba_vs_reference_golden():
     for n, g, rn in zip(names, grads, ref_norms):
         if "grad." + n in gold.files and rn > 10 * floor:
             assert_close(g, gold["grad." + n], 2e-2, "grad." + n)
+
+
+# --------------------------------------------------------------------------------------------------------- fused layer norm
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+@pytest.mark.parametrize("rows,C", [(4096, 48), (1000, 96), (513, 192), (77, 384), (130, 32), (9, 768), (64, 8)],
+                         ids=lambda v: str(v))
+def test_emu_fused_layer_norm(dtype, rows, C):
+    from segmamba_b200.layer_norm import fused_layer_norm, supported
+    torch.manual_seed(rows + C)
+    x = (torch.randn(2, rows, C) * 1.7 + 0.4).to(dtype).requires_grad_()
+    w = (torch.rand(C) + 0.5).requires_grad_()
+    b = (torch.randn(C) * 0.3).requires_grad_()
+    dy = torch.randn(2, rows, C).to(dtype)
+    if not supported(x, C):
+        pytest.skip("shape outside the kernel's vector constraints for this dtype")
+    y = fused_layer_norm(x, w, b, 1e-5)
+    assert y.dtype == dtype and y.shape == x.shape
+    gx, gw, gb = torch.autograd.grad(y, [x, w, b], dy)
+    xr = x.detach().float().requires_grad_()
+    wr, br = w.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    yr = F.layer_norm(xr, (C,), wr, br, 1e-5)
+    rx, rw, rb = torch.autograd.grad(yr, [xr, wr, br], dy.float())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert_close(y, yr, tol, "y")
+    assert_close(gx, rx, 1e-4 if dtype == torch.float32 else 2e-2, "dx")
+    assert_close(gw, rw, 1e-4 if dtype == torch.float32 else 2e-2, "dweight")
+    assert_close(gb, rb, 1e-4 if dtype == torch.float32 else 2e-2, "dbias")
+
+
+def test_emu_fused_layer_norm_large_mean_and_no_bias():
+    from segmamba_b200.layer_norm import fused_layer_norm
+    x = (torch.randn(300, 48) * 0.01 + 30.0)
+    w = torch.ones(48)
+    assert_close(fused_layer_norm(x, w, None, 1e-5), F.layer_norm(x.double(), (48,), eps=1e-5).float(), 2e-3, "mean 30, std 0.01")
+
+
+def test_emu_segmamba_with_fused_layer_norm(monkeypatch):
+    """the full module with the fused LayerNorm switched on equals the module with nn.LayerNorm (forward and parameter grads)."""
+    from segmamba_b200 import layer_norm
+    from segmamba_b200.segmamba import SegMamba
+    c = gi.MODEL_CASE
+    torch.manual_seed(3)
+    m = SegMamba(in_chans=c["in_chans"], out_chans=c["out_chans"], depths=c["depths"], feat_size=c["feat_size"],
+                 hidden_size=c["hidden_size"]).train()
+    x = gi.model_input(c["seed"] + 1, (c["batch"], c["in_chans"], c["spatial"], c["spatial"], c["spatial"]))
+    outs, grads = [], []
+    for on in (False, True):
+        monkeypatch.setattr(layer_norm, "ENABLED", on)
+        out = m(x)
+        g = torch.autograd.grad(out.square().mean(), [p for p in m.parameters()])
+        outs.append(out.detach())
+        grads.append(g)
+    assert_close(outs[1], outs[0], 1e-4, "logits, fused vs nn.LayerNorm")
+    num = sum(float((a.double() - b.double()).pow(2).sum()) for a, b in zip(grads[1], grads[0]))
+    den = sum(float(b.double().pow(2).sum()) for b in grads[0])
+    assert (num / den) ** 0.5 < 1e-3

@@ -1,0 +1,51 @@
+"""GPU parity of the fused LayerNorm (smb_layernorm_fwd / _bwd) against torch's fp32 LayerNorm.
+
+The kernel was written after the last GPU slot of its round and has so far only run on the CPU SIMT emulator
+(tests/test_emu_kernels.py), where it passes; it is therefore off by default (SMB_FUSED_LAYERNORM) and this file sorts last
+and is marked xfail(strict=False): an XPASS here is the first hardware confirmation, a failure does not mask the rest of the
+suite."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import assert_close
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first hardware run of the fused LayerNorm", strict=False)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+@pytest.mark.parametrize("rows,C", [(262144, 48), (32768, 96), (4096, 192), (512, 384), (1000, 32), (77, 768)], ids=lambda v: str(v))
+def test_fused_layer_norm(dtype, rows, C):
+    from segmamba_b200.layer_norm import fused_layer_norm
+    torch.manual_seed(rows + C)
+    x = (torch.randn(2, rows, C, device="cuda") * 1.7 + 0.4).to(dtype).requires_grad_()
+    w = (torch.rand(C, device="cuda") + 0.5).requires_grad_()
+    b = (torch.randn(C, device="cuda") * 0.3).requires_grad_()
+    dy = torch.randn(2, rows, C, device="cuda").to(dtype)
+    y = fused_layer_norm(x, w, b, 1e-5)
+    gx, gw, gb = torch.autograd.grad(y, [x, w, b], dy)
+    xr = x.detach().float().requires_grad_()
+    wr, br = w.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    yr = F.layer_norm(xr, (C,), wr, br, 1e-5)
+    rx, rw, rb = torch.autograd.grad(yr, [xr, wr, br], dy.float())
+    lo = dtype == torch.float32
+    assert_close(y, yr, 1e-5 if lo else 1e-2, "y")
+    assert_close(gx, rx, 1e-4 if lo else 2e-2, "dx")
+    assert_close(gw, rw, 2e-4 if lo else 2e-2, "dweight")
+    assert_close(gb, rb, 2e-4 if lo else 2e-2, "dbias")
+
+
+def test_segmamba_step_with_fused_layer_norm(monkeypatch):
+    import golden_inputs as gi
+    from segmamba_b200 import layer_norm
+    from segmamba_b200.segmamba import SegMamba
+    c = gi.MODEL_CASE
+    torch.manual_seed(3)
+    m = SegMamba(in_chans=4, out_chans=4, depths=c["depths"], feat_size=c["feat_size"], hidden_size=c["hidden_size"]).cuda().train()
+    x = torch.rand(2, 4, 32, 32, 32, device="cuda")
+    outs = []
+    for on in (False, True):
+        monkeypatch.setattr(layer_norm, "ENABLED", on)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs.append(m(x).float())
+    assert_close(outs[1], outs[0], 2e-2, "bf16 logits, fused vs nn.LayerNorm")

@@ -185,6 +185,8 @@ inline float __expf(float x) { return std::exp(x); }
 inline float __logf(float x) { return std::log(x); }
 inline float __fdividef(float a, float b) { return a / b; }
 inline float __frcp_rn(float a) { return 1.f / a; }
+inline float rsqrtf(float a) { return 1.f / std::sqrt(a); }
+inline float __frsqrt_rn(float a) { return 1.f / std::sqrt(a); }
 inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
