@@ -185,10 +185,33 @@ NCU_DRAM_BYTES = {
 _T0 = time.time()
 
 
+_LAST_PROGRESS = [time.time(), "start"]
+
+
 def _log(rank, msg):
-    """progress on stderr (rank 0 only): stdout carries nothing but the final JSON line."""
+    """progress on stderr (rank 0 only): stdout carries nothing but the final JSON line.  Every call also feeds the stall
+    watchdog of multi-rank runs."""
+    _LAST_PROGRESS[0], _LAST_PROGRESS[1] = time.time(), msg
     if rank == 0:
         print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def _start_stall_watchdog(rank, limit_s=420.0):
+    """multi-rank runs only: a collective that never completes would otherwise hold the box until the caller's own timeout.
+    If no progress marker is reached for `limit_s`, dump every thread's stack on stderr and exit non-zero."""
+    import faulthandler
+    import threading
+
+    def watch():
+        while True:
+            time.sleep(5.0)
+            idle = time.time() - _LAST_PROGRESS[0]
+            if idle > limit_s:
+                print(f"[bench rank {rank}] no progress for {idle:.0f}s after '{_LAST_PROGRESS[1]}': giving up", file=sys.stderr, flush=True)
+                faulthandler.dump_traceback(file=sys.stderr)
+                os._exit(3)
+
+    threading.Thread(target=watch, daemon=True, name="bench-stall-watchdog").start()
 
 
 def main_native(args):
@@ -211,9 +234,7 @@ def main_native(args):
         # In-switch reduction (NVLS) is a bonus for a 270 MB gradient all-reduce, not a requirement; its
         # multicast set-up needs fabric-manager support that not every container exposes, so it is opt-in here.
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
-        if rank == 0:                                 # if a collective stalls, say where (stderr; stdout stays the JSON line)
-            import faulthandler
-            faulthandler.dump_traceback_later(300, repeat=True, file=sys.stderr)
+        _start_stall_watchdog(rank, 420.0 + 0.5 * (args.steps + args.warmup))   # if a collective stalls, say where and stop (stderr; stdout stays the JSON line)
         _log(rank, "init_process_group(nccl)")
         dist.init_process_group(backend="nccl", device_id=dev, timeout=datetime.timedelta(minutes=10))
         dist.barrier()
@@ -228,6 +249,7 @@ def main_native(args):
     model.train()
     net = model
     if world > 1:
+        _log(rank, "wrapping the model in DistributedDataParallel")
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
     opt = torch.optim.SGD(model.parameters(), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)   # 3_train.py:51-52
     B, P = args.batch, args.patch
@@ -320,6 +342,7 @@ def main_native(args):
     _log(rank, f"timed region done: {ms_per_step:.2f} ms/step")
     e2e = None
     if not args.no_e2e:
+        _log(rank, "end-to-end leg")
         e2e_step()
         e2e_ms = timed(e2e_step, args.steps) / args.steps
         e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT,
@@ -375,9 +398,7 @@ def main_native(args):
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:
-        if rank == 0:
-            import faulthandler
-            faulthandler.cancel_dump_traceback_later()
+        _log(rank, "done")
         dist.destroy_process_group()
 
 
