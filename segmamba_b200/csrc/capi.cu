@@ -51,6 +51,12 @@ Plan make_plan(int batch, int dim, int L, int N, int G) {
     return pl;
 }
 
+// floats per (P | H | hin | cumP) workspace array, sized for the shortest segment plan_segment may pick
+size_t seg_floats_max(int batch, int dim, int L, int N) {
+    const int smin = smb::seg_min();
+    return align_up((size_t)batch * ((L + smin - 1) / smin) * N * dim, 64);
+}
+
 int check_common(int batch, int dim, int L, int N, int G, int dtype, const char *who) {
     if (batch <= 0 || dim <= 0 || L <= 0) return fail(SMB_EINVAL, "%s: batch, dim and seqlen must be positive", who);
     if (N != 8 && N != 16) return fail(SMB_EUNSUPPORTED, "%s: dstate %d unsupported (8 or 16)", who, N);
@@ -73,9 +79,8 @@ SMB_API size_t smb_scan_fwd_workspace_bytes(int32_t batch, int32_t dim, int32_t 
     // G = 1 gives the smallest S, i.e. the largest segment count.
     const Plan pl = make_plan(batch, dim, seqlen, dstate, 1);
     Plan plmax = pl;
-    // segment count can only shrink with larger S; be conservative and size for S = kCkpt
-    const int nseg_max = (seqlen + smb::kCkpt - 1) / smb::kCkpt;
-    const size_t seg_floats = align_up((size_t)batch * nseg_max * dstate * dim, 64);
+    // segment count can only shrink with larger S; be conservative and size for the shortest segment plan_segment may pick
+    const size_t seg_floats = seg_floats_max(batch, dim, seqlen, dstate);
     return sizeof(float) * (4 * seg_floats + plmax.ck_floats);
 }
 
@@ -108,7 +113,7 @@ SMB_API int smb_scan_fwd(const smb_scan_fwd_args *a, void *cuda_stream) {
     p.B_bs = a->B_bs; p.B_gs = a->B_gs; p.B_ns = a->B_ns; p.B_ls = a->B_ls;
     p.C_bs = a->C_bs; p.C_gs = a->C_gs; p.C_ns = a->C_ns; p.C_ls = a->C_ls;
     float *ws = reinterpret_cast<float *>(a->workspace);
-    const size_t segf = align_up((size_t)a->batch * ((a->seqlen + smb::kCkpt - 1) / smb::kCkpt) * N * a->dim, 64);
+    const size_t segf = seg_floats_max(a->batch, a->dim, a->seqlen, N);
     p.P = ws; p.H = ws + segf; p.hin = ws + 2 * segf; p.cumP = ws + 3 * segf;
     p.hstates = a->hstates ? a->hstates : (a->x ? ws + 4 * segf : nullptr);
     cudaError_t e = smb::scan_fwd_dispatch(p, a->dtype, N, a->z != nullptr, a->x, (cudaStream_t)cuda_stream);

@@ -51,13 +51,23 @@ __device__ __forceinline__ WorkItem decode_work(const ScanP &p, int w) {
     return wi;
 }
 
-// Segment length heuristic (host): largest S in {256..2048} that still yields >= 24 warps per SM (two waves at the
-// 12-warp residency the kernels reach) on a 148-SM B200; S divides 2048 so the reference's 2048-position chunk states fall on segment ends.
+// Segment length heuristic (host): largest S in {seg_min .. 2048} that still yields >= 24 warps per SM (two waves at the
+// 12-warp residency the kernels reach) on a 148-SM B200; S divides 2048 so the reference's 2048-position chunk states fall on
+// segment ends, and divides or is a multiple of kCkpt so checkpoints fall on tile boundaries of exactly one segment.
+// Tuning knobs (read per call, unset = defaults): SMB_SEG_WARPS_PER_SM (24), SMB_SEG_MIN (256; 32 / 64 / 128 allow shorter
+// segments, i.e. more parallelism and shorter serial chains for the small late-stage problems).
+inline int seg_min() {
+    const char *e = getenv("SMB_SEG_MIN");
+    const int v = e ? atoi(e) : kCkpt;
+    return (v == 32 || v == 64 || v == 128) ? v : kCkpt;
+}
 inline int plan_segment(int batch, int n_tiles, int L) {
-    static const long tune = getenv("SMB_SEG_WARPS_PER_SM") ? atol(getenv("SMB_SEG_WARPS_PER_SM")) : 24;   // tuning knob
-    const long target = 148L * tune;
+    const char *e = getenv("SMB_SEG_WARPS_PER_SM");
+    const long tune = e ? atol(e) : 24;
+    const long target = 148L * (tune > 0 ? tune : 24);
+    const int smin = seg_min();
     int S = 2048;
-    while (S > kCkpt && (long)batch * n_tiles * ((L + S - 1) / S) < target) S >>= 1;
+    while (S > smin && (long)batch * n_tiles * ((L + S - 1) / S) < target) S >>= 1;
     return S;
 }
 

@@ -291,3 +291,16 @@ def test_emu_segmamba_with_fused_layer_norm(monkeypatch):
     num = sum(float((a.double() - b.double()).pow(2).sum()) for a, b in zip(grads[1], grads[0]))
     den = sum(float(b.double().pow(2).sum()) for b in grads[0])
     assert (num / den) ** 0.5 < 1e-3
+
+
+@pytest.mark.parametrize("seg_min", ["32", "64", "128"])
+def test_emu_scan_short_segments(monkeypatch, seg_min):
+    """SMB_SEG_MIN tuning knob: segments shorter than the 256-position checkpoint interval (more, shorter serial chains for the
+    small late-stage problems) give the same results, chunk states and checkpoints included."""
+    monkeypatch.setenv("SMB_SEG_MIN", seg_min)
+    for shape, direction in (((2, 40, 700, 16, 1), 0), ((1, 33, 2300, 16, 1), 1), ((2, 48, 512, 8, 2), 0)):
+        batch, dim, L, N, G = shape
+        d = rand_scan_inputs(300 + L, batch, dim, L, N, G, torch.float32, device="cpu")
+        res = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)
+        ref = tg._oracle_fwd_bwd(d, flip=bool(direction))
+        tg._compare(res, ref, torch.float32, True)
