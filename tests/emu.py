@@ -19,7 +19,7 @@ def build_emu_lib() -> str:
     spec = importlib.util.spec_from_file_location("simt_emu_build", os.path.join(ROOT, "tools", "simt_emu", "build.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    return mod.build()
+    return mod.build(asan=os.environ.get("SMB_EMU_ASAN") == "1")     # memcheck mode: see tools/simt_emu/build.py
 
 
 _EMU = None

@@ -54,10 +54,11 @@ def test_emu_scan_random_vs_oracle(dtype, shape, direction):
     tg._compare(res, ref, dtype, True)
 
 
-def test_emu_scan_descending_lane_order():
-    """same kernels with the threads of every block resumed in descending order: a cross-lane shared-memory dependency that
-    lacks a barrier produces a different (wrong) result in one of the two orders."""
-    emu.emu_lib().smb_emu_set_reverse(1)
+@pytest.mark.parametrize("order", [1, 2, 7], ids=["descending", "random2", "random7"])
+def test_emu_scan_other_thread_orders(order):
+    """same kernels with the threads of every block resumed in descending or pseudo-random order: a cross-lane shared-memory
+    dependency that lacks a barrier produces a different (wrong) result under some order."""
+    emu.emu_lib().smb_emu_set_reverse(order)
     d = rand_scan_inputs(9, 2, 40, 900, 16, 1, torch.float32, device="cpu")
     for direction in (0, 1):
         res = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)
@@ -74,6 +75,39 @@ def test_emu_scan_strided_hbl_layout():
         d2[k] = hbl(d[k])
         assert d2[k].stride() == (L, batch * L, 1)
     tg._compare(tg._run_fwd_bwd(d2), tg._oracle_fwd_bwd(d), torch.float32, True)
+
+
+@pytest.mark.parametrize("order", [1, 5], ids=["descending", "random5"])
+def test_emu_norms_and_conv_other_thread_orders(order):
+    from segmamba_b200 import causal_conv1d_cuda as cc
+    from segmamba_b200.instance_norm import fused_instance_norm
+    from segmamba_b200.layer_norm import fused_layer_norm
+    emu.emu_lib().smb_emu_set_reverse(order)
+    orc = _oracle()
+    d = gi.conv_inputs(77, 2, 40, 1300, 4)
+    out = cc.causal_conv1d_fwd(d["x"], d["weight"], d["bias"], True)
+    dx, dw, db = cc.causal_conv1d_bwd(d["x"], d["weight"], d["bias"], d["dout"], None, True)
+    assert_close(out, orc.causal_conv1d_fwd_raw(d["x"], d["weight"], d["bias"], True), 1e-5, "conv out")
+    odx, odw, odb = orc.causal_conv1d_bwd_raw(d["x"], d["weight"], d["bias"], d["dout"], True)
+    assert_close(dx, odx, 1e-4, "conv dx"); assert_close(dw, odw, 1e-4, "conv dw"); assert_close(db, odb, 1e-4, "conv db")
+    x = (torch.randn(2, 48, 8, 8, 8) + 0.5).contiguous(memory_format=torch.channels_last_3d).requires_grad_()
+    a = torch.randn(2, 48, 8, 8, 8).requires_grad_()
+    y = fused_instance_norm(x, "leaky_relu", 0.01, add=a, add_norm=True)
+    g = torch.autograd.grad(y, [x, a], torch.ones_like(y))
+    xr, ar = x.detach().clone().requires_grad_(), a.detach().clone().requires_grad_()
+    yr = F.leaky_relu(F.instance_norm(xr) + F.instance_norm(ar), 0.01)
+    gr = torch.autograd.grad(yr, [xr, ar], torch.ones_like(yr))
+    assert_close(y, yr, 1e-4, "instnorm y"); assert_close(g[0], gr[0], 1e-3, "instnorm dx"); assert_close(g[1], gr[1], 1e-3, "instnorm dx2")
+    t = torch.randn(700, 96).requires_grad_()
+    w, b = torch.rand(96).requires_grad_(), torch.randn(96).requires_grad_()
+    yl = fused_layer_norm(t, w, b)
+    gl = torch.autograd.grad(yl, [t, w, b], torch.ones_like(yl) * 0.3)
+    tr, wr, br = (v.detach().clone().requires_grad_() for v in (t, w, b))
+    ylr = F.layer_norm(tr, (96,), wr, br)
+    glr = torch.autograd.grad(ylr, [tr, wr, br], torch.ones_like(ylr) * 0.3)
+    assert_close(yl, ylr, 1e-5, "layernorm y")
+    for u, v, n in zip(gl, glr, ("dx", "dw", "db")):
+        assert_close(u, v, 2e-4, "layernorm " + n)
 
 
 # ------------------------------------------------------------------------------------------------- conv1d and seq permute

@@ -1,0 +1,46 @@
+#!/bin/bash
+# One gpurun call = validation + A/B measurements + profiles, everything under gpurun_out/<tag>_*.
+#
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh r2a'
+#
+# Stages can be switched off with SKIP="tests ncu ..." (space separated: tests smoke mb bench ab ncu ncufull).
+# Numbers printed under ncu are never bench values; the bench lines come from the plain runs.
+TAG=${1:-s}
+O=gpurun_out
+mkdir -p $O
+skip() { [[ " $SKIP " == *" $1 "* ]]; }
+{ nvidia-smi; nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv; nproc; } > $O/${TAG}_env.txt 2>&1
+
+if ! skip tests; then
+  timeout 900 python -m pytest tests -x -q -m gpu > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_pytest.log
+fi
+if ! skip smoke; then
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1
+fi
+if ! skip mb; then
+  timeout 600 python tools/microbench.py --dtypes bf16,f32 --batches 2 --out $O/${TAG}_mb.json > $O/${TAG}_mb.log 2>&1
+fi
+if ! skip bench; then
+  timeout 600 python bench.py --steps 10 --warmup 3 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
+  timeout 600 python bench.py --steps 10 --warmup 3 --cuda-graph --no-cpu-baseline > $O/${TAG}_bench_graph.json 2> $O/${TAG}_bench_graph.err
+fi
+if ! skip ab; then   # A/B of the opt-in paths against the default, same box, back to back
+  SMB_FUSED_LAYERNORM=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_ln.json 2> $O/${TAG}_bench_ln.err
+  for s in 32 64 128; do
+    SMB_SEG_MIN=$s timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_segmin$s.json 2> $O/${TAG}_bench_segmin$s.err
+  done
+  SMB_FUSED_LAYERNORM=1 timeout 300 python -m pytest tests/test_gpu_zz_layernorm.py -q > $O/${TAG}_pytest_ln.log 2>&1
+  timeout 300 python tools/op_breakdown.py > $O/${TAG}_breakdown.log 2>&1
+fi
+if ! skip ncu; then  # launch list of one training step (kernel shares)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/${TAG}_launches_step.csv \
+      python tools/profile_step.py --what step > $O/${TAG}_ncu_step.log 2>&1
+  python tools/launch_summary.py $O/${TAG}_launches_step.csv > $O/${TAG}_launches_step_summary.txt 2>&1
+fi
+if ! skip ncufull; then  # one full capture of the scan kernels (stage 0, training batch)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_ -c 8 -o $O/${TAG}_scan_full -f \
+      python tools/profile_step.py --what scan > $O/${TAG}_ncu_scan.log 2>&1
+  ncu -i $O/${TAG}_scan_full.ncu-rep --page raw --csv > $O/${TAG}_scan_raw.csv 2>/dev/null
+  python tools/ncu_raw_summary.py $O/${TAG}_scan_raw.csv > $O/${TAG}_scan_summary.txt 2>&1
+fi
+ls -la $O | tail -40

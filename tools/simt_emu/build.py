@@ -110,8 +110,13 @@ def transform(text: str) -> str:
     return rewrite_launches(text)
 
 
-def build(verbose: bool = False, opt: str = "-O1") -> str:
-    gen = os.path.join(BUILD, "gen")
+def build(verbose: bool = False, opt: str = "-O1", asan: bool = False) -> str:
+    """asan=True: AddressSanitizer build (libsegmamba_b200_emu_asan.so) -- out-of-bounds reads / writes of any kernel on the
+    (host) tensors abort with a report; run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0."""
+    global OUT
+    if asan:
+        OUT = os.path.join(BUILD, "libsegmamba_b200_emu_asan.so")
+    gen = os.path.join(BUILD, "gen_asan" if asan else "gen")
     os.makedirs(gen, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     deps += [os.path.join(HERE, f) for f in ("simt_emu.h", "simt_emu.cpp", "build.py")] + [os.path.join(ROOT, "include", "segmamba_b200.h")]
@@ -128,6 +133,8 @@ def build(verbose: bool = False, opt: str = "-O1") -> str:
         cpps.append(dst)
     cpps.append(os.path.join(HERE, "simt_emu.cpp"))
     flags = ["-std=c++17", opt, "-g", "-fPIC", "-DSMB_EMU=1", "-fno-strict-aliasing", "-w", "-I", HERE, "-I", CSRC, "-I", CUDA_INC]
+    if asan:
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
     procs, objs = [], []
     for cpp in cpps:                                             # one compiler process per translation unit, in parallel
         obj = os.path.join(gen, os.path.basename(cpp)[:-4] + ".o")
@@ -140,9 +147,11 @@ def build(verbose: bool = False, opt: str = "-O1") -> str:
         if p.wait() != 0:
             raise subprocess.CalledProcessError(p.returncode, cmd)
     # -Bsymbolic: the stubbed CUDA runtime entry points must bind inside this library even when a real libcudart is loaded
-    subprocess.run(["/usr/bin/g++", "-shared", "-o", OUT] + objs + ["-lpthread", "-Wl,-Bsymbolic"], check=True)
+    subprocess.run(["/usr/bin/g++", "-shared", "-o", OUT] + objs + ["-lpthread", "-Wl,-Bsymbolic"] + (["-fsanitize=address"] if asan else []),
+                   check=True)
     return OUT
 
 
 if __name__ == "__main__":
-    print(build(verbose=True, opt=sys.argv[1] if len(sys.argv) > 1 else "-O1"))
+    args = [a for a in sys.argv[1:] if a != "--asan"]
+    print(build(verbose=True, opt=args[0] if args else "-O1", asan="--asan" in sys.argv))

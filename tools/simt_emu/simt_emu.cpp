@@ -36,22 +36,44 @@ smb_emu_switch:
 )");
 #endif
 
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>
+#define SMB_EMU_ASAN 1
+#endif
+
 namespace emu {
 
 thread_local Block *g_block = nullptr;
+
+// AddressSanitizer has to be told about every stack switch (build.py --asan: the memcheck mode of the emulator)
+struct StackInfo { const void *bottom; size_t size; };
+static thread_local StackInfo g_sched_stack = {nullptr, 0};
+
+static inline void switch_stacks(void **save_sp, void *load_sp, const StackInfo *to, bool dying) {
+#ifdef SMB_EMU_ASAN
+    void *fake = nullptr;
+    __sanitizer_start_switch_fiber(dying ? nullptr : &fake, to->bottom, to->size);
+#endif
+    smb_emu_switch(save_sp, load_sp);
+#ifdef SMB_EMU_ASAN
+    __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#endif
+}
 
 static size_t stack_bytes() {
     static const size_t v = (getenv("SMB_EMU_STACK_KB") ? (size_t)atol(getenv("SMB_EMU_STACK_KB")) : 256) * 1024;
     return v;
 }
+// resume order of a block's threads: 0 ascending, 1 descending, >= 2 pseudo-random per scheduling round (value = seed)
 static std::atomic<int> g_reverse{-1};
-static bool reverse_order() {
+static int g_order_mode() {
     int v = g_reverse.load();
     if (v < 0) {
-        v = getenv("SMB_EMU_REVERSE") && atoi(getenv("SMB_EMU_REVERSE")) != 0;
+        v = getenv("SMB_EMU_REVERSE") ? atoi(getenv("SMB_EMU_REVERSE")) : 0;
+        if (v < 0) v = 0;
         g_reverse.store(v);
     }
-    return v != 0;
+    return v;
 }
 static int worker_count() {
     static const int v = getenv("SMB_EMU_THREADS") ? atoi(getenv("SMB_EMU_THREADS")) : (int)std::thread::hardware_concurrency();
@@ -71,7 +93,7 @@ void yield_wait(State st, unsigned mask) {
     f.st = st;
     f.wait_mask = mask;
 #ifdef SMB_EMU_FAST_SWITCH
-    smb_emu_switch(&f.sp, b->sched_sp);
+    switch_stacks(&f.sp, b->sched_sp, &g_sched_stack, false);
 #else
     swapcontext(&f.ctx, &b->sched);
 #endif
@@ -100,12 +122,20 @@ bool lane_live_and_in_mask(int src_lane, unsigned mask) {
 }
 
 static void fiber_entry() {
+#ifdef SMB_EMU_ASAN
+    {   // first time on this stack: complete the switch the scheduler started and learn the scheduler's stack bounds
+        const void *bottom = nullptr;
+        size_t size = 0;
+        __sanitizer_finish_switch_fiber(nullptr, &bottom, &size);
+        g_sched_stack = {bottom, size};
+    }
+#endif
     Block *b = g_block;
     (*b->body)();
     Fiber &f = b->fibers[b->cur];
     f.st = DONE;
 #ifdef SMB_EMU_FAST_SWITCH
-    smb_emu_switch(&f.sp, b->sched_sp);     // never resumed
+    switch_stacks(&f.sp, b->sched_sp, &g_sched_stack, true);     // never resumed
     abort();
 #endif
     // ucontext: returning resumes uc_link (the scheduler)
@@ -138,18 +168,30 @@ static void run_block(Block &b, unsigned char *stacks) {
         makecontext(&f.ctx, fiber_entry, 0);
 #endif
     }
-    const bool rev = reverse_order();
+    const int order = g_order_mode();
     const int nwarps = (n + 31) / 32;
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    uint64_t rng = 0x9e3779b97f4a7c15ull ^ ((uint64_t)blockIdx.x * 0x100000001b3ull) ^ (uint64_t)order;
     for (;;) {
         bool ran = false;
+        if (order >= 2) {                                   // a fresh pseudo-random resume order for every scheduling round
+            for (int i = n - 1; i > 0; --i) {
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                std::swap(perm[i], perm[(int)(rng % (uint64_t)(i + 1))]);
+            }
+        }
         for (int k = 0; k < n; ++k) {
-            const int i = rev ? n - 1 - k : k;
+            const int i = order >= 2 ? perm[k] : (order == 1 ? n - 1 - k : k);
             Fiber &f = b.fibers[i];
             if (f.st != READY) continue;
             b.cur = i;
             threadIdx = f.tid;
 #ifdef SMB_EMU_FAST_SWITCH
-            smb_emu_switch(&b.sched_sp, f.sp);
+            {
+                const StackInfo fs = {stacks + (size_t)i * ss, ss};
+                switch_stacks(&b.sched_sp, f.sp, &fs, false);
+            }
 #else
             swapcontext(&b.sched, &f.ctx);
 #endif
@@ -250,8 +292,9 @@ void run_grid(const std::function<void()> &body, dim3 grid, dim3 block, size_t s
 
 }  // namespace emu
 
-// resume order of the threads of a block: 0 ascending, 1 descending (tests run both to expose missing barriers)
-extern "C" __attribute__((visibility("default"))) void smb_emu_set_reverse(int on) { emu::g_reverse.store(on ? 1 : 0); }
+// resume order of the threads of a block: 0 ascending, 1 descending, >= 2 pseudo-random (tests run several to expose
+// missing barriers)
+extern "C" __attribute__((visibility("default"))) void smb_emu_set_reverse(int mode) { emu::g_reverse.store(mode < 0 ? 0 : mode); }
 
 // ---- the slice of the CUDA runtime the sources call: "device" memory is host memory, streams are synchronous ----
 extern "C" {
