@@ -357,7 +357,19 @@ static cudaError_t launch_fwd_n(const ScanP &p, int N, bool has_z, float *x, cud
     return launch_fwd<T, 8>(p, has_z, x, st);
 }
 
+cudaError_t x_finalize_launch(const ScanP &p, int N, float *x, cudaStream_t st) {
+    const int n_chunks = (p.L + 2047) / 2048;
+    const int64_t total = (int64_t)p.batch * p.dim * n_chunks * N;
+    x_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.hstates, p.cumP, x, p.batch, p.dim, N, p.L, p.S, p.n_seg, p.nck,
+                                                                      n_chunks); count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t scan_fwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, float *x, cudaStream_t st) {
+    {   // opt-in software-pipelined kernels for 16-bit activations (read per call: a tuning switch, not an API)
+        const char *v2 = getenv("SMB_FWD_V2");
+        if (dtype != 0 && v2 && v2[0] == '1') return scan_fwd_v2_dispatch(p, dtype, N, has_z, x, st);
+    }
     switch (dtype) {
         case 0: return launch_fwd_n<float>(p, N, has_z, x, st);
         case 1: return launch_fwd_n<__half>(p, N, has_z, x, st);

@@ -72,6 +72,9 @@ inline int plan_segment(int batch, int n_tiles, int L) {
 }
 
 cudaError_t scan_fwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, float *x, cudaStream_t st);
+// software-pipelined (cp.async) variant for 16-bit activations, scan_fwd_v2.cu; chosen by scan_fwd_dispatch when SMB_FWD_V2=1
+cudaError_t scan_fwd_v2_dispatch(const ScanP &p, int dtype, int N, bool has_z, float *x, cudaStream_t st);
+cudaError_t x_finalize_launch(const ScanP &p, int N, float *x, cudaStream_t st);
 cudaError_t scan_fwd_agg_dispatch(const ScanP &p, int dtype, int N, cudaStream_t st);
 cudaError_t scan_bwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, cudaStream_t st);
 cudaError_t carry_launch(const float *P, const float *H, float *hin, float *cumP, int batch, int n_seg, int N, int dim,

@@ -338,3 +338,45 @@ def test_emu_scan_short_segments(monkeypatch, seg_min):
         res = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)
         ref = tg._oracle_fwd_bwd(d, flip=bool(direction))
         tg._compare(res, ref, torch.float32, True)
+
+
+# ----------------------------------------------------------------------------- software-pipelined forward scan (SMB_FWD_V2=1)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("shape", [(2, 40, 700, 16, 1), (1, 33, 31, 16, 1), (2, 48, 600, 8, 2), (1, 64, 2304, 16, 1), (1, 32, 256, 16, 1)],
+                         ids=lambda s: "b%d_d%d_L%d_n%d_g%d" % s)
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_emu_scan_fwd_v2_vs_oracle(monkeypatch, dtype, shape, direction):
+    """cp.async double-buffered forward kernels: same results as the oracle (and hence as the default kernels); the emulator
+    defers every cp.async until the issuing thread waits for it, so a missing wait or barrier shows up as NaN poison."""
+    monkeypatch.setenv("SMB_FWD_V2", "1")
+    batch, dim, L, N, G = shape
+    d = rand_scan_inputs(100 + L, batch, dim, L, N, G, dtype, device="cpu")
+    res = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)     # the backward consumes the v2 forward's hstates
+    ref = tg._oracle_fwd_bwd(d, flip=bool(direction))
+    tg._compare(res, ref, dtype, True)
+
+
+@pytest.mark.parametrize("order", [1, 3], ids=["descending", "random3"])
+def test_emu_scan_fwd_v2_thread_orders_and_layouts(monkeypatch, order):
+    from segmamba_b200 import selective_scan_cuda as ssc
+    monkeypatch.setenv("SMB_FWD_V2", "1")
+    emu.emu_lib().smb_emu_set_reverse(order)
+    batch, dim, L, N = 2, 64, 1504, 16
+    d = rand_scan_inputs(7, batch, dim, L, N, 1, torch.bfloat16, device="cpu")
+    hbl = lambda t: t.permute(1, 0, 2).contiguous().permute(1, 0, 2)            # the mixer's channel-major layout
+    d2 = dict(d)
+    for k in ("u", "delta", "z", "dout"):
+        d2[k] = hbl(d[k])
+    for direction in (0, 1):
+        res = tg._run_fwd_bwd(d2, direction=direction, use_hstates=True)
+        tg._compare(res, tg._oracle_fwd_bwd(d, flip=bool(direction)), torch.bfloat16, True)
+    # same arithmetic as the default kernels (up to FMA contraction choices of the compiler), with and without z / out
+    B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
+    v2 = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, want_out=True, want_x=True, want_hstates=True)
+    v2n = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], None, d["delta_bias"], True, want_out=True, want_x=False)
+    monkeypatch.setenv("SMB_FWD_V2", "0")
+    v1 = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, want_out=True, want_x=True, want_hstates=True)
+    v1n = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], None, d["delta_bias"], True, want_out=True, want_x=False)
+    for a, b, tol in zip(v2, v1, (8e-3, 1e-5, 8e-3, 1e-5)):          # (out, x, out_z, hstates): one bf16 ulp / fp32 round-off
+        assert_close(a, b, tol, "pipelined vs default kernels")
+    assert_close(v2n[0], v1n[0], 8e-3, "pipelined vs default kernels, no z")

@@ -1,16 +1,16 @@
-"""GPU parity of the fused LayerNorm (smb_layernorm_fwd / _bwd) against torch's fp32 LayerNorm.
+"""First hardware runs of the opt-in kernels: the fused LayerNorm (smb_layernorm_fwd / _bwd, SMB_FUSED_LAYERNORM=1) against
+torch's fp32 LayerNorm, and the software-pipelined forward scan (SMB_FWD_V2=1) against the default kernels.
 
-The kernel was written after the last GPU slot of its round and has so far only run on the CPU SIMT emulator
-(tests/test_emu_kernels.py), where it passes; it is therefore off by default (SMB_FUSED_LAYERNORM) and this file sorts last
-and is marked xfail(strict=False): an XPASS here is the first hardware confirmation, a failure does not mask the rest of the
-suite."""
+Both were written after the last GPU slot of their round and have so far only run on the CPU SIMT emulator
+(tests/test_emu_kernels.py), where they pass; they are therefore off by default, and this file sorts last and is marked
+xfail(strict=False): an XPASS here is the first hardware confirmation, a failure does not mask the rest of the suite."""
 import pytest
 import torch
 import torch.nn.functional as F
 
 from util import assert_close
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first hardware run of the fused LayerNorm", strict=False)]
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first hardware run of an opt-in kernel", strict=False)]
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
@@ -49,3 +49,24 @@ def test_segmamba_step_with_fused_layer_norm(monkeypatch):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             outs.append(m(x).float())
     assert_close(outs[1], outs[0], 2e-2, "bf16 logits, fused vs nn.LayerNorm")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_scan_fwd_v2_matches_default(monkeypatch, dtype, direction):
+    """software-pipelined forward kernels (SMB_FWD_V2=1; emulator-validated, first hardware run): same outputs, chunk states
+    and checkpoints as the default kernels, at a ragged small size and at the stage-0 size."""
+    from segmamba_b200 import selective_scan_cuda as ssc
+    from util import rand_scan_inputs
+    for (batch, dim, L) in ((2, 40, 5000), (2, 96, 262144)):
+        d = rand_scan_inputs(17, batch, dim, L, 16, 1, dtype)
+        B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
+        run = lambda: ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, direction=direction,
+                                 want_out=True, want_x=True, want_hstates=True)
+        monkeypatch.setenv("SMB_FWD_V2", "0")
+        ref = run()
+        monkeypatch.setenv("SMB_FWD_V2", "1")
+        got = run()
+        torch.cuda.synchronize()
+        for a, b, tol, n in zip(got, ref, (8e-3, 1e-5, 8e-3, 1e-5), ("out", "x", "out_z", "hstates")):
+            assert_close(a, b, tol, n)

@@ -121,6 +121,25 @@ bool lane_live_and_in_mask(int src_lane, unsigned mask) {
     return (b->fibers[b->cur].last_part >> src_lane) & 1;     // took part in the same collective (it may have exited since)
 }
 
+void cp_async_issue(void *smem_dst, const void *gmem_src, unsigned bytes) {
+    Fiber &f = g_block->fibers[g_block->cur];
+    if (bytes != 4 && bytes != 8 && bytes != 16) die("cp.async size must be 4, 8 or 16 bytes");
+    if (((uintptr_t)smem_dst | (uintptr_t)gmem_src) & (bytes - 1)) die("cp.async source / destination not aligned to the copy size");
+    f.async.push_back({smem_dst, gmem_src, bytes, f.async_group});
+}
+void cp_async_commit() { g_block->fibers[g_block->cur].async_group++; }
+void cp_async_wait(int allow_pending_groups) {
+    Fiber &f = g_block->fibers[g_block->cur];
+    const int done_below = f.async_group - allow_pending_groups;      // groups with index < done_below must be complete
+    size_t keep = 0;
+    for (size_t i = 0; i < f.async.size(); ++i) {
+        const Fiber::AsyncCopy &a = f.async[i];
+        if (a.group < done_below) memcpy(a.dst, a.src, a.bytes);
+        else f.async[keep++] = a;
+    }
+    f.async.resize(keep);
+}
+
 static void fiber_entry() {
 #ifdef SMB_EMU_ASAN
     {   // first time on this stack: complete the switch the scheduler started and learn the scheduler's stack bounds
@@ -133,6 +152,7 @@ static void fiber_entry() {
     Block *b = g_block;
     (*b->body)();
     Fiber &f = b->fibers[b->cur];
+    if (!f.async.empty()) die("thread exits with cp.async copies that were never waited for");
     f.st = DONE;
 #ifdef SMB_EMU_FAST_SWITCH
     switch_stacks(&f.sp, b->sched_sp, &g_sched_stack, true);     // never resumed
@@ -149,6 +169,8 @@ static void run_block(Block &b, unsigned char *stacks) {
         f.st = READY;
         f.seq = 0;
         f.wait_mask = 0;
+        f.async.clear();
+        f.async_group = 0;
         const unsigned x = i % blockDim.x, y = (i / blockDim.x) % blockDim.y, z = i / (blockDim.x * blockDim.y);
         f.tid = make_uint3(x, y, z);
 #ifdef SMB_EMU_FAST_SWITCH

@@ -58,6 +58,9 @@ struct Fiber {
     uint3 tid;
     int seq = 0;                       // number of warp collectives this lane has entered (double-buffer parity)
     unsigned last_part = 0;            // lanes that took part in this lane's most recent collective
+    struct AsyncCopy { void *dst; const void *src; unsigned bytes; int group; };
+    std::vector<AsyncCopy> async;      // cp.async copies issued but not yet waited for (performed at wait time, see below)
+    int async_group = 0;               // index of the group currently being filled (cp.async.commit_group increments it)
 };
 
 struct Block {
@@ -157,6 +160,16 @@ inline int __all_sync(unsigned mask, int pred) {
     return 1;
 }
 inline unsigned __activemask() { return 0xffffffffu; }
+
+// ---- cp.async (LDGSTS).  The copy is DEFERRED until the issuing thread waits for its group: code that reads the destination
+// without cp.async.wait_group / wait_all sees the NaN poison instead of data, and a thread that exits with copies in flight
+// aborts -- the two ways such a pipeline goes wrong on hardware.  Visibility to other lanes still needs the barrier that the
+// thread-order modes check.
+namespace emu {
+void cp_async_issue(void *smem_dst, const void *gmem_src, unsigned bytes);
+void cp_async_commit();
+void cp_async_wait(int allow_pending_groups);
+}  // namespace emu
 
 // ---- atomics (blocks run on several OS threads) -----------------------------------------------------
 inline float atomicAdd(float *addr, float val) {
