@@ -50,7 +50,8 @@ def test_library_exports_match_header():
 @pytest.mark.parametrize("cname,pyname", [("smb_scan_fwd_args", "ScanFwdArgs"), ("smb_scan_bwd_args", "ScanBwdArgs"),
                                           ("smb_conv1d_args", "Conv1dArgs"), ("smb_conv1d_bwd_args", "Conv1dBwdArgs"),
                                           ("smb_seq_permute_args", "SeqPermuteArgs"), ("smb_instnorm_args", "InstNormArgs"),
-                                          ("smb_instnorm_bwd_args", "InstNormBwdArgs")])
+                                          ("smb_instnorm_bwd_args", "InstNormBwdArgs"), ("smb_layernorm_args", "LayerNormArgs"),
+                                          ("smb_layernorm_bwd_args", "LayerNormBwdArgs")])
 def test_ctypes_structs_match_header(cname, pyname):
     from segmamba_b200 import _lib
     py = [f[0] for f in getattr(_lib, pyname)._fields_]
@@ -78,6 +79,12 @@ def test_no_cpu_fallback():
         causal_conv1d_cuda.causal_conv1d_fwd(u, torch.randn(4, 4), None, True)
     with pytest.raises(RuntimeError):
         causal_conv1d_cuda.causal_conv1d_update(u[:, :, 0], torch.zeros(1, 4, 4), torch.randn(4, 4), None, True)
+    from segmamba_b200.instance_norm import fused_instance_norm
+    from segmamba_b200.layer_norm import fused_layer_norm
+    with pytest.raises(RuntimeError):
+        fused_instance_norm(torch.randn(1, 8, 4, 4, 4))
+    with pytest.raises(RuntimeError):
+        fused_layer_norm(torch.randn(16, 48), torch.ones(48), torch.zeros(48))
 
 
 def test_missing_library_fails_loudly(monkeypatch):
