@@ -33,6 +33,7 @@ if ! skip ab; then   # A/B of the opt-in paths against the default, same box, ba
   done
   SMB_FUSED_LAYERNORM=1 timeout 300 python -m pytest tests/test_gpu_zz_layernorm.py -q > $O/${TAG}_pytest_ln.log 2>&1
   timeout 300 python tools/op_breakdown.py > $O/${TAG}_breakdown.log 2>&1
+  timeout 900 python tools/ref_equivalent_step.py --native --steps 5 --out $O/${TAG}_ref_equivalent_step.json > $O/${TAG}_ref_equivalent_step.log 2>&1
 fi
 if ! skip ncu; then  # launch list of one training step (kernel shares)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/${TAG}_launches_step.csv \
