@@ -19,6 +19,8 @@
 #include "scan_internal.h"
 #include "scan_steps.cuh"
 
+#include <type_traits>
+
 namespace smb {
 
 constexpr int kBwdWarps = 8;               // channels per CTA in R3
@@ -26,38 +28,6 @@ constexpr int kRowPad = kCkpt + 32;        // padded smem row: position p lives 
 static_assert(kRun * 32 == kCkpt, "R3 chunk must equal the checkpoint interval");
 
 __device__ __forceinline__ int pad_pos(int p) { return p + ((p >> 5) << 2); }
-
-// one reverse position for all states (pairs packed):  mu = a (mu + g C)
-template <int N, int QL, int JN>
-__device__ __forceinline__ void ragg_step_chunk(const float *s_C, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
-                                                float2 (&mu)[N / 2]) {
-    const float4 c4 = bc_read4_c<N, QL, JN>(s_C);
-    const float2 a0 = decay2<2 * JN>(__fmul2_rn(dt2, A2[2 * JN]));
-    const float2 a1 = decay2<2 * JN + 1>(__fmul2_rn(dt2, A2[2 * JN + 1]));
-    mu[2 * JN] = __fmul2_rn(a0, __ffma2_rn(g2, f2(c4.x, c4.y), mu[2 * JN]));
-    mu[2 * JN + 1] = __fmul2_rn(a1, __ffma2_rn(g2, f2(c4.z, c4.w), mu[2 * JN + 1]));
-}
-template <int N, int QL>
-__device__ __forceinline__ void ragg_step(const float *s_C, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
-                                          float2 (&mu)[N / 2]) {
-    ragg_step_chunk<N, QL, 0>(s_C, dt2, g2, A2, mu);
-    ragg_step_chunk<N, QL, 1>(s_C, dt2, g2, A2, mu);
-    if (N == 16) {
-        ragg_step_chunk<N, QL, (N == 16 ? 2 : 0)>(s_C, dt2, g2, A2, mu);
-        ragg_step_chunk<N, QL, (N == 16 ? 3 : 1)>(s_C, dt2, g2, A2, mu);
-    }
-}
-// 8 consecutive positions walked in descending order (compile-time local index QL = 7..0)
-template <int N, int QL>
-__device__ __forceinline__ void ragg_block(const float *blkC, const float (&gg)[8], const float (&dd)[8], const float2 (&A2)[N / 2],
-                                           float2 (&mu)[N / 2], float &sumdt) {
-    if constexpr (QL >= 0) {
-        const float dt = dd[QL], g = gg[QL];
-        sumdt += dt;
-        ragg_step<N, QL>(blkC, f2(dt, dt), f2(g, g), A2, mu);
-        ragg_block<N, QL - 1>(blkC, gg, dd, A2, mu, sumdt);
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // R1: reverse aggregate per chunk (lane == channel)
@@ -776,8 +746,13 @@ static cudaError_t launch_bwd(const ScanP &p, cudaStream_t st) {
     // R1
     const int ctas = (p.n_work + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t sm1 = (size_t)kWarpsPerCta * (3 * kTile * kTile + kTile * N) * sizeof(float);
-    SMB_SET_SMEM_ONCE((scan_bwd_ragg_kernel<T, N, kHasZ>), sm1);
-    scan_bwd_ragg_kernel<T, N, kHasZ><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
+    const char *r1v2 = getenv("SMB_RAGG_V2");                 // opt-in software-pipelined R1 for 16-bit activations (scan_bwd_v2.cu)
+    if (sizeof(T) == 2 && r1v2 && r1v2[0] == '1') {
+        if ((e = scan_bwd_ragg_v2_dispatch(p, sizeof(T) == 2 && std::is_same<T, __half>::value ? 1 : 2, N, kHasZ, st)) != cudaSuccess) return e;
+    } else {
+        SMB_SET_SMEM_ONCE((scan_bwd_ragg_kernel<T, N, kHasZ>), sm1);
+        scan_bwd_ragg_kernel<T, N, kHasZ><<<ctas, kWarpsPerCta * 32, sm1, st>>>(p); count_launch();
+    }
     // R2
     if ((e = carry_launch(p.Pb, p.Mloc, p.Min, nullptr, p.batch, p.nck, N, p.dim, 1, st)) != cudaSuccess) return e;
     if (p.stash && !(kHasZ && p.out_z)) {

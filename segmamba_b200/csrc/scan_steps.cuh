@@ -77,4 +77,39 @@ __device__ __forceinline__ void main_block(const float *blkB, const float *blkC,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// reverse aggregate (R1 of the backward pass)
+// ---------------------------------------------------------------------------------------------
+// one reverse position for all states (pairs packed):  mu = a (mu + g C)
+template <int N, int QL, int JN>
+__device__ __forceinline__ void ragg_step_chunk(const float *s_C, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
+                                                float2 (&mu)[N / 2]) {
+    const float4 c4 = bc_read4_c<N, QL, JN>(s_C);
+    const float2 a0 = decay2<2 * JN>(__fmul2_rn(dt2, A2[2 * JN]));
+    const float2 a1 = decay2<2 * JN + 1>(__fmul2_rn(dt2, A2[2 * JN + 1]));
+    mu[2 * JN] = __fmul2_rn(a0, __ffma2_rn(g2, f2(c4.x, c4.y), mu[2 * JN]));
+    mu[2 * JN + 1] = __fmul2_rn(a1, __ffma2_rn(g2, f2(c4.z, c4.w), mu[2 * JN + 1]));
+}
+template <int N, int QL>
+__device__ __forceinline__ void ragg_step(const float *s_C, float2 dt2, float2 g2, const float2 (&A2)[N / 2],
+                                          float2 (&mu)[N / 2]) {
+    ragg_step_chunk<N, QL, 0>(s_C, dt2, g2, A2, mu);
+    ragg_step_chunk<N, QL, 1>(s_C, dt2, g2, A2, mu);
+    if (N == 16) {
+        ragg_step_chunk<N, QL, (N == 16 ? 2 : 0)>(s_C, dt2, g2, A2, mu);
+        ragg_step_chunk<N, QL, (N == 16 ? 3 : 1)>(s_C, dt2, g2, A2, mu);
+    }
+}
+// 8 consecutive positions walked in descending order (compile-time local index QL = 7..0)
+template <int N, int QL>
+__device__ __forceinline__ void ragg_block(const float *blkC, const float (&gg)[8], const float (&dd)[8], const float2 (&A2)[N / 2],
+                                           float2 (&mu)[N / 2], float &sumdt) {
+    if constexpr (QL >= 0) {
+        const float dt = dd[QL], g = gg[QL];
+        sumdt += dt;
+        ragg_step<N, QL>(blkC, f2(dt, dt), f2(g, g), A2, mu);
+        ragg_block<N, QL - 1>(blkC, gg, dd, A2, mu, sumdt);
+    }
+}
+
 }  // namespace smb

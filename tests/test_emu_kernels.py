@@ -380,3 +380,29 @@ def test_emu_scan_fwd_v2_thread_orders_and_layouts(monkeypatch, order):
     for a, b, tol in zip(v2, v1, (8e-3, 1e-5, 8e-3, 1e-5)):          # (out, x, out_z, hstates): one bf16 ulp / fp32 round-off
         assert_close(a, b, tol, "pipelined vs default kernels")
     assert_close(v2n[0], v1n[0], 8e-3, "pipelined vs default kernels, no z")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("shape", [(2, 40, 700, 16, 1), (1, 33, 31, 16, 1), (2, 48, 600, 8, 2), (1, 64, 2304, 16, 1)],
+                         ids=lambda s: "b%d_d%d_L%d_n%d_g%d" % s)
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_emu_scan_ragg_v2_vs_oracle(monkeypatch, dtype, shape, direction):
+    """software-pipelined R1 (SMB_RAGG_V2=1) together with the pipelined forward: full forward + both backward paths."""
+    monkeypatch.setenv("SMB_RAGG_V2", "1")
+    monkeypatch.setenv("SMB_FWD_V2", "1")
+    batch, dim, L, N, G = shape
+    d = rand_scan_inputs(100 + L, batch, dim, L, N, G, dtype, device="cpu")
+    for has_z in (True, False):
+        res = tg._run_fwd_bwd(d, has_z=has_z, direction=direction, use_hstates=True)
+        ref = tg._oracle_fwd_bwd(d, has_z=has_z, flip=bool(direction))
+        tg._compare(res, ref, dtype, has_z)
+
+
+def test_emu_scan_ragg_v2_thread_orders(monkeypatch):
+    monkeypatch.setenv("SMB_RAGG_V2", "1")
+    d = rand_scan_inputs(9, 2, 40, 900, 16, 1, torch.bfloat16, device="cpu")
+    for order in (1, 4):
+        emu.emu_lib().smb_emu_set_reverse(order)
+        for direction in (0, 1):
+            res = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)
+            tg._compare(res, tg._oracle_fwd_bwd(d, flip=bool(direction)), torch.bfloat16, True)

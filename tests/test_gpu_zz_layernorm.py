@@ -70,3 +70,23 @@ def test_scan_fwd_v2_matches_default(monkeypatch, dtype, direction):
         torch.cuda.synchronize()
         for a, b, tol, n in zip(got, ref, (8e-3, 1e-5, 8e-3, 1e-5), ("out", "x", "out_z", "hstates")):
             assert_close(a, b, tol, n)
+
+
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_scan_ragg_v2_matches_default(monkeypatch, direction):
+    """software-pipelined R1 (SMB_RAGG_V2=1): the backward's gradients equal the default path's at the stage-0 size."""
+    from segmamba_b200 import selective_scan_cuda as ssc
+    from util import rand_scan_inputs
+    d = rand_scan_inputs(19, 2, 96, 262144, 16, 1, torch.bfloat16)
+    B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
+    _, _, _, hst = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, direction=direction,
+                              want_out=False, want_x=False, want_hstates=True)
+    run = lambda: ssc.bwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], d["dout"], None, True, False,
+                             direction=direction, hstates=hst)
+    monkeypatch.setenv("SMB_RAGG_V2", "0")
+    ref = run()
+    monkeypatch.setenv("SMB_RAGG_V2", "1")
+    got = run()
+    torch.cuda.synchronize()
+    for a, b, n in zip(got[:8], ref[:8], ("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias", "dz")):
+        assert_close(a, b, 1e-2, n)
