@@ -23,7 +23,6 @@ import math
 import os
 import subprocess
 
-import numpy as np
 import torch
 import torch.nn.functional as F
 

@@ -18,7 +18,6 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import layer_norm
 from .instance_norm import fused_instance_norm

@@ -14,7 +14,6 @@ dB/dC come back already reduced over channels.  There is no CPU path: non-CUDA t
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 from torch.amp import custom_bwd, custom_fwd
 
 from . import causal_conv1d_cuda, selective_scan_cuda

@@ -1,5 +1,4 @@
 """GPU parity of the native causal conv1d and the inter-slice permutation."""
-import numpy as np
 import pytest
 import torch
 

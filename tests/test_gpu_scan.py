@@ -1,6 +1,5 @@
 """GPU parity of the native selective scan (through the selective_scan_cuda drop-in -> C ABI) against the CPU
 oracle and the committed golden vectors (reference outputs)."""
-import numpy as np
 import pytest
 import torch
 

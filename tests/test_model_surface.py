@@ -1,6 +1,5 @@
 """CPU checks of the nn.Module surface: state_dict keys / shapes / order identical to the reference's (fixture written by
 oracle/gen_golden.py from the reference class), constructor defaults, and the sliding-window host logic."""
-import numpy as np
 import torch
 
 import golden_inputs as gi

@@ -3,7 +3,6 @@ mirror TTA against the whole-volume-flip definition, and window sharding over a 
 import os
 
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

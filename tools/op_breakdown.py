@@ -1,5 +1,4 @@
 """Per-op, per-shape device time of the native calls inside one training step (CUDA events around every C-ABI call)."""
-import json
 import os
 import sys
 
