@@ -16,9 +16,11 @@ pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first hardware run of a
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
 @pytest.mark.parametrize("rows,C", [(262144, 48), (32768, 96), (4096, 192), (512, 384), (1000, 32), (77, 768)], ids=lambda v: str(v))
 def test_fused_layer_norm(dtype, rows, C):
-    from segmamba_b200.layer_norm import fused_layer_norm
+    from segmamba_b200.layer_norm import fused_layer_norm, supported
     torch.manual_seed(rows + C)
     x = (torch.randn(2, rows, C, device="cuda") * 1.7 + 0.4).to(dtype).requires_grad_()
+    if not supported(x, C):
+        pytest.skip("more than 128 sixteen-byte vectors per row for this dtype")
     w = (torch.rand(C, device="cuda") + 0.5).requires_grad_()
     b = (torch.randn(C, device="cuda") * 0.3).requires_grad_()
     dy = torch.randn(2, rows, C, device="cuda").to(dtype)
