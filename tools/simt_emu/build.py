@@ -135,20 +135,22 @@ def build(verbose: bool = False, opt: str = "-O1", asan: bool = False) -> str:
     flags = ["-std=c++17", opt, "-g", "-fPIC", "-DSMB_EMU=1", "-fno-strict-aliasing", "-w", "-I", HERE, "-I", CSRC, "-I", CUDA_INC]
     if asan:
         flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)                                  # a preloaded libasan (memcheck runs) must not instrument the compiler
     procs, objs = [], []
     for cpp in cpps:                                             # one compiler process per translation unit, in parallel
         obj = os.path.join(gen, os.path.basename(cpp)[:-4] + ".o")
         cmd = ["/usr/bin/g++"] + flags + ["-c", cpp, "-o", obj]
         if verbose:
             print(" ".join(cmd))
-        procs.append((cmd, subprocess.Popen(cmd)))
+        procs.append((cmd, subprocess.Popen(cmd, env=env)))
         objs.append(obj)
     for cmd, p in procs:
         if p.wait() != 0:
             raise subprocess.CalledProcessError(p.returncode, cmd)
     # -Bsymbolic: the stubbed CUDA runtime entry points must bind inside this library even when a real libcudart is loaded
     subprocess.run(["/usr/bin/g++", "-shared", "-o", OUT] + objs + ["-lpthread", "-Wl,-Bsymbolic"] + (["-fsanitize=address"] if asan else []),
-                   check=True)
+                   check=True, env=env)
     return OUT
 
 
