@@ -14,6 +14,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import statistics
 import sys
 import threading
@@ -375,6 +376,19 @@ def main_native(args):
 
     roofline = roof("scan_fwd", scan_fwd_bytes)
     roof_bwd = roof("scan_bwd", scan_bwd_bytes)
+    # The forward scan is co-bound by the MUFU pipe: one ex2 per (b, d, t, n) update in each of its two passes.
+    # Extra key, not part of the contract: ex2 throughput against 148 SMs x 16 lanes/clk at the SM clock sampled under load.
+    roof_mufu = None
+    try:
+        if roofline and clocks and clocks.get("sm_mhz"):
+            b_, d_, l_, n_ = [int(v) for v in re.findall(r"batch=(\d+) dim=(\d+) L=(\d+) N=(\d+)", roofline["kernel"])[0]]
+            ex2 = 2.0 * b_ * d_ * l_ * n_
+            ach = ex2 / (roofline["avg_ms"] * 1e-3) / 1e12
+            peak = 148 * 16 * float(clocks["sm_mhz"]) * 1e6 / 1e12
+            roof_mufu = {"bound": "mufu", "achieved": ach, "peak": peak, "unit": "Tex2/s", "frac": ach / peak,
+                         "ex2_per_call": ex2, "kernel": roofline["kernel"]}
+    except Exception:
+        roof_mufu = None
     native_ms = {}
     prof_steps = args.steps if graphed is None else 2
     for (op, meta), d in durs.items():
@@ -390,6 +404,7 @@ def main_native(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_scan_bwd": roof_bwd,
+            "roofline_mufu": roof_mufu,
             "native_ms_per_step": native_ms,
             "host_enqueue_ms_per_step": host_ms,
         }
