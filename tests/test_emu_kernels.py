@@ -406,3 +406,42 @@ def test_emu_scan_ragg_v2_thread_orders(monkeypatch):
         for direction in (0, 1):
             res = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)
             tg._compare(res, tg._oracle_fwd_bwd(d, flip=bool(direction)), torch.bfloat16, True)
+
+
+# ------------------------------------------------------------------------------------------- properties and inference path
+def test_emu_scan_linearity_and_reverse_equals_flip():
+    """size-independent properties: y is linear in u for fixed delta, B, C; direction=1 equals the op on flipped operands."""
+    from segmamba_b200 import selective_scan_cuda as ssc
+    d = rand_scan_inputs(5, 2, 40, 1000, 16, 1, torch.float32, device="cpu")
+    B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
+    f = lambda u, direction=0: ssc.fwd_ex(u, d["delta"], d["A"], B, C, None, None, d["delta_bias"], True, direction=direction, want_x=False)[0]
+    u2 = torch.randn_like(d["u"])
+    assert_close(f(0.7 * d["u"] - 1.3 * u2), 0.7 * f(d["u"]) - 1.3 * f(u2), 1e-5, "linearity in u")
+    fl = lambda t: t.flip(-1).contiguous()
+    rev = f(d["u"], direction=1)
+    ref = ssc.fwd_ex(fl(d["u"]), fl(d["delta"]), d["A"], fl(B), fl(C), None, None, d["delta_bias"], True, want_x=False)[0].flip(-1)
+    assert_close(rev, ref, 1e-6, "reverse walk vs flipped operands")
+
+
+def test_emu_sliding_window_with_segmamba():
+    """the GPU-resident sliding-window driver with the native model as predictor (eval mode, no_grad), against a window-by-window
+    evaluation with explicit gaussian accumulation; mirror TTA keeps shape and finiteness."""
+    from segmamba_b200 import sliding_window as sw
+    from segmamba_b200.segmamba import SegMamba
+    c = gi.MODEL_CASE
+    torch.manual_seed(0)
+    m = SegMamba(in_chans=4, out_chans=4, depths=c["depths"], feat_size=c["feat_size"], hidden_size=c["hidden_size"]).eval()
+    x = torch.rand(1, 4, 40, 48, 33)
+    with torch.no_grad():
+        out = sw.sliding_window_inference(x, (32, 32, 32), 2, m, overlap=0.5, mode="gaussian")
+        assert out.shape == (1, 4, 40, 48, 33)
+        starts = sw.window_starts((40, 48, 33), (32, 32, 32), 0.5)
+        w = sw.gaussian_importance_map((32, 32, 32))[None, None]
+        acc, cnt = torch.zeros_like(out), torch.zeros(1, 1, 40, 48, 33)
+        for (a, b, cc) in starts:
+            sl = (slice(None), slice(None), slice(a, a + 32), slice(b, b + 32), slice(cc, cc + 32))
+            acc[sl] += m(x[sl].contiguous()) * w
+            cnt[sl] += w
+        assert torch.allclose(out, acc / cnt, rtol=1e-3, atol=1e-4)
+        tta = sw.sliding_window_inference(x, (32, 32, 32), 2, m, mirror_axes=(0,))
+        assert tta.shape == out.shape and torch.isfinite(tta).all()
