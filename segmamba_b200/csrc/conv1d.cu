@@ -9,7 +9,10 @@
 
 namespace smb {
 
-constexpr int kConvThreads = 128;
+#ifndef SMB_CONV_THREADS
+#define SMB_CONV_THREADS 128
+#endif
+constexpr int kConvThreads = SMB_CONV_THREADS;
 
 __device__ __forceinline__ float silu_grad(float o) {   // d/do [o * sigmoid(o)]
     const float s = sigmoidf(o);

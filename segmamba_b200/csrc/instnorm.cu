@@ -19,6 +19,15 @@
 namespace smb {
 
 constexpr int kNormThreads = 256;
+#ifndef SMB_IN_FWD_MINB
+#define SMB_IN_FWD_MINB 3
+#endif
+#ifndef SMB_IN_BWD_MINB0
+#define SMB_IN_BWD_MINB0 3
+#endif
+#ifndef SMB_IN_BWD_MINB2
+#define SMB_IN_BWD_MINB2 2
+#endif
 
 __device__ __forceinline__ float act_fwd(float v, int act, float slope) {
     if (act == 1) return v > 0.f ? v : 0.f;
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(1024) in_finalize_fwd_kernel(const float *__re
 // forward apply: y = act( (x - mean) rstd  [+ (x2 - mean2) rstd2 | + x2] )
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, 3) in_apply_fwd_kernel(const NormP p) {
+__global__ void __launch_bounds__(kNormThreads, SMB_IN_FWD_MINB) in_apply_fwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     const int C = p.channels, CV = C / V;
     const RowMap m = row_map(p, CV);
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(kNormThreads, 3) in_apply_fwd_kernel(const Nor
 // partial layout: [batch][cta][3][C]
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? 3 : 2)) in_stats_bwd_kernel(const NormP p) {
+__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : SMB_IN_BWD_MINB2)) in_stats_bwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     extern __shared__ float sm[];
     const int C = p.channels, CV = C / V;
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(1024) in_finalize_bwd_kernel(const float *__re
 
 // backward apply: dx = rstd (g - mean g - xhat mean(g xhat)) ;  dx2 likewise (mode 2) or dx2 = g (mode 1)
 template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? 3 : 2)) in_apply_bwd_kernel(const NormP p) {
+__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : SMB_IN_BWD_MINB2)) in_apply_bwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     const int C = p.channels, CV = C / V;
     const RowMap m = row_map(p, CV);

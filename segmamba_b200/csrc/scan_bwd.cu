@@ -121,7 +121,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
 // grid = (chunks, channel octets (group-aligned), batch)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int N, bool kHasZ>
+#ifdef SMB_R3_MINB
+__global__ void __launch_bounds__(kBwdWarps * 32, SMB_R3_MINB) scan_bwd_main_kernel(const ScanP p) {
+#else
 __global__ void __launch_bounds__(kBwdWarps * 32) scan_bwd_main_kernel(const ScanP p) {
+#endif
     extern __shared__ __align__(16) float smem[];
     float *sB = smem;                                  // [N][kRowPad]
     float *sC = sB + N * kRowPad;                      // [N][kRowPad]

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(1024) carry_kernel(const float *__restrict__ P
 // pass 3
 // ---------------------------------------------------------------------------------------------
 template <typename T, int N, bool kHasZ>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main_kernel(const ScanP p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, SMB_FWD_MAIN_MINB) scan_fwd_main_kernel(const ScanP p) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * kWarpsPerCta + warp;

@@ -7,7 +7,15 @@
 
 namespace smb {
 
-constexpr int kWarpsPerCta = 4;   // independent warps per CTA in the lane-per-channel kernels
+// Build-time tuning knobs (tools/build_variants.py builds alternative libraries with -D overrides; the defaults are the
+// hardware-verified configuration and leave the generated code unchanged).
+#ifndef SMB_WARPS_PER_CTA
+#define SMB_WARPS_PER_CTA 4
+#endif
+#ifndef SMB_FWD_MAIN_MINB
+#define SMB_FWD_MAIN_MINB 3
+#endif
+constexpr int kWarpsPerCta = SMB_WARPS_PER_CTA;   // independent warps per CTA in the lane-per-channel kernels
 
 struct ScanP {
     int batch, dim, L, G;

@@ -3,7 +3,7 @@
 #
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh r2a'
 #
-# Stages can be switched off with SKIP="tests ncu ..." (space separated: tests smoke mb bench ab ncu ncufull).
+# Stages can be switched off with SKIP="tests ncu ..." (space separated: tests smoke mb bench ab variants ncu ncufull).
 # Numbers printed under ncu are never bench values; the bench lines come from the plain runs.
 TAG=${1:-s}
 O=gpurun_out
@@ -36,6 +36,14 @@ if ! skip ab; then   # A/B of the opt-in paths against the default, same box, ba
   SMB_FUSED_LAYERNORM=1 timeout 300 python -m pytest tests/test_gpu_zz_layernorm.py -q > $O/${TAG}_pytest_ln.log 2>&1
   timeout 300 python tools/op_breakdown.py > $O/${TAG}_breakdown.log 2>&1
   timeout 900 python tools/ref_equivalent_step.py --native --steps 5 --out $O/${TAG}_ref_equivalent_step.json > $O/${TAG}_ref_equivalent_step.log 2>&1
+fi
+if ! skip variants; then   # build-time tuning variants, if tools/build_variants.py was run before the call
+  for lib in segmamba_b200/variants/lib_*.so; do
+    [ -e "$lib" ] || continue
+    v=$(basename $lib .so)
+    SMB_LIB=$PWD/$lib timeout 300 python tools/microbench.py --dtypes bf16 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_$v.json > $O/${TAG}_mb_$v.log 2>&1
+    SMB_LIB=$PWD/$lib timeout 300 python tools/op_breakdown.py > $O/${TAG}_breakdown_$v.log 2>&1
+  done
 fi
 if ! skip ncu; then  # launch list of one training step (kernel shares)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/${TAG}_launches_step.csv \
