@@ -5,6 +5,8 @@
 // 512..1024-element chunks; here the grid also spans L (each thread owns a run of 8 scan positions, the
 // 3-element halo comes from the neighbouring lane by shuffle), so a 96-channel x 262144-token call fills
 // the chip.  Any width 2..4 is handled as width 4 with leading zero taps.
+#include <cstdlib>
+
 #include "conv_internal.h"
 
 namespace smb {
@@ -214,6 +216,10 @@ static cudaError_t conv_launch_t(const ConvP &p, bool bwd, cudaStream_t st) {
 }
 
 cudaError_t conv1d_dispatch(const ConvP &p, int dtype, bool bwd, cudaStream_t st) {
+    {   // opt-in wide-run kernels for 16-bit activations (read per call: a tuning switch, not an API)
+        const char *v2 = getenv("SMB_CONV_V2");
+        if (dtype != 0 && v2 && v2[0] == '1') return conv1d_v2_dispatch(p, dtype, bwd, st);
+    }
     switch (dtype) {
         case 0: return conv_launch_t<float>(p, bwd, st);
         case 1: return conv_launch_t<__half>(p, bwd, st);

@@ -445,3 +445,31 @@ def test_emu_sliding_window_with_segmamba():
         assert torch.allclose(out, acc / cnt, rtol=1e-3, atol=1e-4)
         tta = sw.sliding_window_inference(x, (32, 32, 32), 2, m, mirror_axes=(0,))
         assert tta.shape == out.shape and torch.isfinite(tta).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("shape", [(2, 40, 1300, 4), (1, 33, 1031, 3), (2, 8, 7, 2), (1, 5, 4096, 4), (1, 3, 17, 4)], ids=lambda s: "b%d_d%d_L%d_w%d" % s)
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_emu_conv_v2_vs_oracle(monkeypatch, dtype, shape, direction):
+    """16-positions-per-thread conv1d kernels for 16-bit activations (SMB_CONV_V2=1): forward, dx (in place), dweight, dbias."""
+    from segmamba_b200 import causal_conv1d_cuda as cc
+    monkeypatch.setenv("SMB_CONV_V2", "1")
+    orc = _oracle()
+    batch, dim, L, width = shape
+    d = gi.conv_inputs(200 + L, batch, dim, L, width)
+    x, dout, w, b = d["x"].to(dtype), d["dout"].to(dtype), d["weight"], d["bias"]
+    xz = torch.empty(2 * dim, batch, L, dtype=dtype).permute(1, 0, 2)
+    xz[:, :dim] = x
+    xv = xz[:, :dim]
+    dxz = torch.zeros_like(xz)
+    for silu in (True, False):
+        out = cc.causal_conv1d_fwd_ex(xv, w, b, silu, direction=direction)
+        dx, dw, db = cc.causal_conv1d_bwd_ex(xv, w, b, dout, dxz[:, :dim], silu, direction=direction)
+        f = (lambda t: t.flip(-1)) if direction else (lambda t: t)
+        o = f(orc.causal_conv1d_fwd_raw(f(x.float()), w, b, silu))
+        odx, odw, odb = orc.causal_conv1d_bwd_raw(f(x.float()), w, b, f(dout.float()), silu)
+        assert_close(out, o, TOL[dtype], "out")
+        assert_close(dxz[:, :dim], f(odx), GRAD_TOL[dtype], "dx (in place)")
+        assert float(dxz[:, dim:].abs().max()) == 0.0
+        assert_close(dw, odw, GRAD_TOL[dtype], "dweight")
+        assert_close(db, odb, GRAD_TOL[dtype], "dbias")

@@ -92,3 +92,28 @@ def test_scan_ragg_v2_matches_default(monkeypatch, direction):
     torch.cuda.synchronize()
     for a, b, n in zip(got[:8], ref[:8], ("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias", "dz")):
         assert_close(a, b, 1e-2, n)
+
+
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_conv_v2_matches_default(monkeypatch, direction):
+    """16-positions-per-thread conv1d (SMB_CONV_V2=1) against the default kernels at the stage-0 size, channel-major views."""
+    import golden_inputs as gi
+    from segmamba_b200 import causal_conv1d_cuda as cc
+    batch, dim, L = 2, 96, 262144
+    d = gi.conv_inputs(23, batch, dim, L, 4)
+    x = torch.empty(dim, batch, L, dtype=torch.bfloat16, device="cuda").permute(1, 0, 2)
+    x.copy_(d["x"].to(torch.bfloat16).cuda())
+    dout = d["dout"].to(torch.bfloat16).cuda()
+    w, b = d["weight"].cuda(), d["bias"].cuda()
+
+    def run():
+        out = cc.causal_conv1d_fwd_ex(x, w, b, True, direction=direction)
+        return (out,) + tuple(cc.causal_conv1d_bwd_ex(x, w, b, dout, None, True, direction=direction))
+    monkeypatch.setenv("SMB_CONV_V2", "0")
+    ref = run()
+    monkeypatch.setenv("SMB_CONV_V2", "1")
+    got = run()
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])          # same per-position arithmetic
+    assert_close(got[2], ref[2], 1e-3, "dweight")
+    assert_close(got[3], ref[3], 1e-3, "dbias")
