@@ -166,4 +166,50 @@ __device__ __forceinline__ void unit_dt(float (&dd)[8], float bias, bool softplu
     }
 }
 
+// ---- token-ascending tile layout: what a TMA box copy produces.  Slot s of a row holds token tok0 + s, where tok0 is the lowest
+// token of the tile (j0 for a forward walk, L - 32 - j0 for a reversed one); scan position p of the tile lives in slot p
+// (forward) or 31 - p (reversed).  Same 64-byte rows and 16-byte-unit swizzle as above. ----
+__device__ __forceinline__ void reverse8(float (&v)[8]) {
+    float t;
+    t = v[0]; v[0] = v[7]; v[7] = t;
+    t = v[1]; v[1] = v[6]; v[6] = t;
+    t = v[2]; v[2] = v[5]; v[5] = t;
+    t = v[3]; v[3] = v[4]; v[4] = t;
+}
+template <typename T, bool kRev> __device__ __forceinline__ void read_unit_asc(const unsigned char *tile, int lane, int u8, float (&v)[8]) {
+    unpack8<T>(*reinterpret_cast<const uint4 *>(tile + raw_unit_off(lane, kRev ? 3 - u8 : u8)), v);
+    if (kRev) reverse8(v);
+}
+template <typename T, bool kRev> __device__ __forceinline__ void write_unit_asc(unsigned char *tile, int lane, int u8, float (&v)[8]) {
+    if (kRev) reverse8(v);
+    *reinterpret_cast<uint4 *>(tile + raw_unit_off(lane, kRev ? 3 - u8 : u8)) = pack8<T>(v);
+}
+// full tile, 8-byte aligned rows: row0 points at (row 0, token tok0)
+template <typename T>
+__device__ __forceinline__ void store_asc_fast(const unsigned char *tile, T *row0, int64_t row_stride, int nrows, int lane) {
+    const int r0 = lane >> 3, c = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int row = r0 + 4 * it;
+        if (row < nrows) *reinterpret_cast<uint2 *>(row0 + (int64_t)row * row_stride + 4 * c) = *reinterpret_cast<const uint2 *>(tile + raw_chunk_off(row, c));
+    }
+}
+template <typename T, bool kRev>
+__device__ __forceinline__ void store_asc_sync(const unsigned char *tile, T *base, int64_t row_stride, int nrows, int j0, int L, int lane) {
+    const int r0 = lane >> 3, c = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int row = r0 + 4 * it;
+        if (row >= nrows) continue;
+        T vals[4];
+        *reinterpret_cast<uint2 *>(vals) = *reinterpret_cast<const uint2 *>(tile + raw_chunk_off(row, c));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int slot = 4 * c + e;
+            const int pos = j0 + (kRev ? kTile - 1 - slot : slot);
+            if (pos < L) base[(int64_t)row * row_stride + (kRev ? L - 1 - pos : pos)] = vals[e];
+        }
+    }
+}
+
 }  // namespace smb

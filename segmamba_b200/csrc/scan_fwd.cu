@@ -368,7 +368,7 @@ cudaError_t x_finalize_launch(const ScanP &p, int N, float *x, cudaStream_t st) 
 cudaError_t scan_fwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, float *x, cudaStream_t st) {
     {   // opt-in software-pipelined kernels for 16-bit activations (read per call: a tuning switch, not an API)
         const char *v2 = getenv("SMB_FWD_V2");
-        if (dtype != 0 && v2 && v2[0] == '1') return scan_fwd_v2_dispatch(p, dtype, N, has_z, x, st);
+        if (dtype != 0 && v2 && (v2[0] == '1' || v2[0] == '2')) return scan_fwd_v2_dispatch(p, dtype, N, has_z, x, v2[0] - '0', st);
     }
     switch (dtype) {
         case 0: return launch_fwd_n<float>(p, N, has_z, x, st);

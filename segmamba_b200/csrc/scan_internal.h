@@ -80,8 +80,9 @@ inline int plan_segment(int batch, int n_tiles, int L) {
 }
 
 cudaError_t scan_fwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, float *x, cudaStream_t st);
-// software-pipelined (cp.async) variant for 16-bit activations, scan_fwd_v2.cu; chosen by scan_fwd_dispatch when SMB_FWD_V2=1
-cudaError_t scan_fwd_v2_dispatch(const ScanP &p, int dtype, int N, bool has_z, float *x, cudaStream_t st);
+// software-pipelined variant for 16-bit activations, scan_fwd_v2.cu; chosen by scan_fwd_dispatch when SMB_FWD_V2 = 1 (tiles
+// staged with cp.async) or 2 (tiles staged with TMA bulk tensor copies + mbarrier; falls back to 1 if a tensor map cannot be built)
+cudaError_t scan_fwd_v2_dispatch(const ScanP &p, int dtype, int N, bool has_z, float *x, int mode, cudaStream_t st);
 cudaError_t x_finalize_launch(const ScanP &p, int N, float *x, cudaStream_t st);
 cudaError_t scan_fwd_agg_dispatch(const ScanP &p, int dtype, int N, cudaStream_t st);
 // software-pipelined R1 (reverse aggregate) for 16-bit activations, scan_bwd_v2.cu; chosen by launch_bwd when SMB_RAGG_V2=1

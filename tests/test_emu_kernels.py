@@ -473,3 +473,35 @@ def test_emu_conv_v2_vs_oracle(monkeypatch, dtype, shape, direction):
         assert float(dxz[:, dim:].abs().max()) == 0.0
         assert_close(dw, odw, GRAD_TOL[dtype], "dweight")
         assert_close(db, odb, GRAD_TOL[dtype], "dbias")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("shape", [(2, 40, 704, 16, 1), (1, 33, 31, 16, 1), (2, 48, 600, 8, 1), (1, 64, 2304, 16, 1), (1, 16, 264, 16, 1)],
+                         ids=lambda s: "b%d_d%d_L%d_n%d_g%d" % s)
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_emu_scan_fwd_tma_vs_oracle(monkeypatch, dtype, shape, direction):
+    """TMA mode of the pipelined forward kernels (SMB_FWD_V2=2): tiles staged by cp.async.bulk.tensor with the 64-byte swizzle and
+    hardware zero fill of ragged tiles, completion through an mbarrier.  The emulator performs the box copies when a thread waits
+    on the barrier and aborts if the byte count differs from expect_tx."""
+    monkeypatch.setenv("SMB_FWD_V2", "2")
+    batch, dim, L, N, G = shape
+    d = rand_scan_inputs(100 + L, batch, dim, L, N, G, dtype, device="cpu")
+    for has_z in (True, False):
+        res = tg._run_fwd_bwd(d, has_z=has_z, direction=direction, use_hstates=True)
+        ref = tg._oracle_fwd_bwd(d, has_z=has_z, flip=bool(direction))
+        tg._compare(res, ref, dtype, has_z)
+
+
+def test_emu_scan_fwd_tma_layouts_and_orders(monkeypatch):
+    monkeypatch.setenv("SMB_FWD_V2", "2")
+    batch, dim, L, N = 2, 64, 1504, 16
+    d = rand_scan_inputs(7, batch, dim, L, N, 1, torch.bfloat16, device="cpu")
+    hbl = lambda t: t.permute(1, 0, 2).contiguous().permute(1, 0, 2)            # channel-major: batch stride < channel stride
+    d2 = dict(d)
+    for k in ("u", "delta", "z", "dout"):
+        d2[k] = hbl(d[k])
+    for order in (0, 1, 6):
+        emu.emu_lib().smb_emu_set_reverse(order)
+        for direction in (0, 1):
+            res = tg._run_fwd_bwd(d2, direction=direction, use_hstates=True)
+            tg._compare(res, tg._oracle_fwd_bwd(d, flip=bool(direction)), torch.bfloat16, True)

@@ -53,10 +53,11 @@ def test_segmamba_step_with_fused_layer_norm(monkeypatch):
     assert_close(outs[1], outs[0], 2e-2, "bf16 logits, fused vs nn.LayerNorm")
 
 
+@pytest.mark.parametrize("mode", ["1", "2"], ids=["cp_async", "tma"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
-def test_scan_fwd_v2_matches_default(monkeypatch, dtype, direction):
-    """software-pipelined forward kernels (SMB_FWD_V2=1; emulator-validated, first hardware run): same outputs, chunk states
+def test_scan_fwd_v2_matches_default(monkeypatch, dtype, direction, mode):
+    """software-pipelined forward kernels (SMB_FWD_V2=1 / 2; emulator-validated, first hardware run): same outputs, chunk states
     and checkpoints as the default kernels, at a ragged small size and at the stage-0 size."""
     from segmamba_b200 import selective_scan_cuda as ssc
     from util import rand_scan_inputs
@@ -67,7 +68,7 @@ def test_scan_fwd_v2_matches_default(monkeypatch, dtype, direction):
                                  want_out=True, want_x=True, want_hstates=True)
         monkeypatch.setenv("SMB_FWD_V2", "0")
         ref = run()
-        monkeypatch.setenv("SMB_FWD_V2", "1")
+        monkeypatch.setenv("SMB_FWD_V2", mode)             # 1: cp.async staging, 2: TMA bulk tensor copies + mbarrier
         got = run()
         torch.cuda.synchronize()
         for a, b, tol, n in zip(got, ref, (8e-3, 1e-5, 8e-3, 1e-5), ("out", "x", "out_z", "hstates")):

@@ -31,6 +31,7 @@ if ! skip ab; then   # A/B of the opt-in paths against the default, same box, ba
   SMB_FWD_V2=1 SMB_RAGG_V2=1 SMB_CONV_V2=1 SMB_FUSED_LAYERNORM=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_all_optin.json 2> $O/${TAG}_bench_all_optin.err
   SMB_FWD_V2=1 SMB_RAGG_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_fwdv2_raggv2.json 2> $O/${TAG}_bench_fwdv2_raggv2.err
   SMB_RAGG_V2=1 timeout 300 python tools/microbench.py --dtypes bf16 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_raggv2.json > $O/${TAG}_mb_raggv2.log 2>&1
+  SMB_FWD_V2=2 timeout 300 python tools/microbench.py --dtypes bf16 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_fwdtma.json > $O/${TAG}_mb_fwdtma.log 2>&1
   SMB_FWD_V2=1 timeout 300 python tools/microbench.py --dtypes bf16 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_fwdv2.json > $O/${TAG}_mb_fwdv2.log 2>&1
   for s in 32 64 128; do
     SMB_SEG_MIN=$s timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_segmin$s.json 2> $O/${TAG}_bench_segmin$s.err

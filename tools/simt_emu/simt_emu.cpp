@@ -140,6 +140,100 @@ void cp_async_wait(int allow_pending_groups) {
     f.async.resize(keep);
 }
 
+// ---- TMA + mbarrier model -----------------------------------------------------------------------------------------
+struct TmapDescEmu {              // must match smb::TmapDesc (csrc/tma.cuh)
+    const void *base;
+    int rank, elem_bytes, swizzle64;
+    uint64_t dims[5];
+    uint64_t strides[5];
+    uint32_t box[5];
+};
+static Block::BarState &bar_state(uint64_t *bar) {
+    Block *b = g_block;
+    for (auto &s : b->bars)
+        if (s.bar == bar) return s;
+    die("mbarrier used before mbarrier.init");
+}
+void mbar_init(uint64_t *bar, int count) {
+    Block *b = g_block;
+    if (count != 1) die("the emulator models single-arrival mbarriers only");
+    for (auto &s : b->bars)
+        if (s.bar == bar) { s = {bar, 0, 0, 0}; return; }
+    b->bars.push_back({bar, 0, 0, 0});
+}
+void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    Block::BarState &s = bar_state(bar);
+    if (s.expected) die("mbarrier.arrive.expect_tx on a phase that is already armed");
+    s.expected = bytes;
+}
+void tma_load(void *smem_dst, const void *tensor_map, const int *coords, int ncoords, uint64_t *bar) {
+    Block *b = g_block;
+    Block::PendingTma p;
+    p.dst = smem_dst;
+    memcpy(p.map, tensor_map, 128);
+    for (int i = 0; i < 5; ++i) p.coords[i] = i < ncoords ? coords[i] : 0;
+    p.ncoords = ncoords;
+    p.bar = bar;
+    (void)bar_state(bar);
+    if ((uintptr_t)((unsigned char *)smem_dst - b->dyn_smem) & 127) die("TMA destination must be 128-byte aligned in shared memory");
+    b->tma.push_back(p);
+}
+static void tma_perform(Block *b, const Block::PendingTma &p, Block::BarState &s) {
+    TmapDescEmu d;
+    memcpy(&d, p.map, sizeof(d));
+    if (d.rank != p.ncoords) die("TMA coordinate count differs from the tensor map's rank");
+    const size_t inner_bytes = (size_t)d.box[0] * d.elem_bytes;
+    size_t rows = 1;
+    for (int i = 1; i < d.rank; ++i) rows *= d.box[i];
+    const size_t dst_off0 = (size_t)((unsigned char *)p.dst - b->dyn_smem);
+    if (d.swizzle64 && (inner_bytes != 64 || (dst_off0 & 511))) die("SWIZZLE_64B tile: 64-byte inner box and 512-byte aligned destination expected");
+    for (size_t r = 0; r < rows; ++r) {
+        size_t rem = r;                                          // box coordinates of this row in dims 1..rank-1
+        bool inb = true;
+        int64_t off = 0;
+        for (int i = 1; i < d.rank; ++i) {
+            const int64_t idx = (int64_t)p.coords[i] + (int64_t)(rem % d.box[i]);
+            rem /= d.box[i];
+            if (idx < 0 || idx >= (int64_t)d.dims[i]) inb = false;
+            off += idx * (int64_t)d.strides[i - 1];
+        }
+        for (uint32_t e = 0; e < d.box[0]; ++e) {
+            const int64_t i0 = (int64_t)p.coords[0] + e;
+            size_t o = dst_off0 + r * inner_bytes + (size_t)e * d.elem_bytes;
+            if (d.swizzle64) o ^= ((o >> 7) & 3) << 4;           // 16-byte chunk index ^= shared-address bits 7..8
+            unsigned char *dst = b->dyn_smem + o;
+            if (inb && i0 >= 0 && i0 < (int64_t)d.dims[0]) memcpy(dst, (const unsigned char *)d.base + off + i0 * d.elem_bytes, d.elem_bytes);
+            else memset(dst, 0, d.elem_bytes);
+        }
+    }
+    s.arrived += (unsigned)(rows * inner_bytes);
+}
+void mbar_wait(uint64_t *bar, unsigned parity) {
+    Block *b = g_block;
+    for (int spins = 0;; ++spins) {
+        Block::BarState &s = bar_state(bar);
+        if ((unsigned)(s.completed & 1) != parity) return;      // the phase with this parity has completed
+        if (s.expected) {                                        // armed: the queued copies that signal it land now
+            size_t keep = 0;
+            for (size_t i = 0; i < b->tma.size(); ++i) {
+                if (b->tma[i].bar == bar) tma_perform(b, b->tma[i], s);
+                else b->tma[keep++] = b->tma[i];
+            }
+            b->tma.resize(keep);
+            if (s.arrived > s.expected) die("more TMA bytes landed on an mbarrier than its expect_tx announced");
+            if (s.arrived == s.expected) {
+                s.completed++;
+                s.expected = 0;
+                s.arrived = 0;
+                return;
+            }
+        }
+        // not armed yet, or copies still to be issued by a thread that has not run: let the others run (try_wait spin)
+        if (spins > 200000) die("mbarrier wait never completed (phase not armed, or fewer bytes issued than expect_tx)");
+        yield_wait(READY, 0);
+    }
+}
+
 static void fiber_entry() {
 #ifdef SMB_EMU_ASAN
     {   // first time on this stack: complete the switch the scheduler started and learn the scheduler's stack bounds
@@ -153,6 +247,11 @@ static void fiber_entry() {
     (*b->body)();
     Fiber &f = b->fibers[b->cur];
     if (!f.async.empty()) die("thread exits with cp.async copies that were never waited for");
+    if (!b->tma.empty()) {
+        bool mine_last = true;
+        for (const Fiber &o : b->fibers) mine_last = mine_last && (&o == &f || o.st == DONE);
+        if (mine_last) die("block exits with TMA copies in flight that nobody waited for");
+    }
     f.st = DONE;
 #ifdef SMB_EMU_FAST_SWITCH
     switch_stacks(&f.sp, b->sched_sp, &g_sched_stack, true);     // never resumed
@@ -289,8 +388,8 @@ void run_grid(const std::function<void()> &body, dim3 grid, dim3 block, size_t s
         b.part.assign((size_t)((nthreads + 31) / 32) * 2, 0);
         b.body = &body;
         std::unique_ptr<unsigned char[]> stacks(new unsigned char[(size_t)nthreads * stack_bytes()]);   // untouched pages cost nothing
-        std::vector<unsigned char> smem(smem_bytes + 256);
-        b.dyn_smem = (unsigned char *)(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127);
+        std::vector<unsigned char> smem(smem_bytes + 2048);
+        b.dyn_smem = (unsigned char *)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);     // CTA shared windows are 1 KB aligned
         g_block = &b;
         gridDim = grid;
         blockDim = block;
@@ -299,6 +398,8 @@ void run_grid(const std::function<void()> &body, dim3 grid, dim3 block, size_t s
             if (id >= nblocks) break;
             blockIdx = make_uint3((unsigned)(id % grid.x), (unsigned)((id / grid.x) % grid.y), (unsigned)(id / ((long)grid.x * grid.y)));
             memset(b.dyn_smem, 0xff, smem_bytes);                       // NaN poison: shared memory is not zero on entry
+            b.tma.clear();
+            b.bars.clear();
             run_block(b, stacks.get());
         }
         g_block = nullptr;

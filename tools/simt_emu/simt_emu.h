@@ -73,6 +73,10 @@ struct Block {
     std::vector<unsigned> part;        // [warp][parity] participants of the collective, recorded at release time
     unsigned char *dyn_smem = nullptr;
     const std::function<void()> *body = nullptr;
+    struct PendingTma { void *dst; unsigned char map[128]; int coords[5]; int ncoords; uint64_t *bar; };
+    std::vector<PendingTma> tma;       // bulk tensor copies issued, not yet performed
+    struct BarState { uint64_t *bar; unsigned expected, arrived; int completed; };
+    std::vector<BarState> bars;        // mbarrier bookkeeping, keyed by shared-memory address
 };
 
 extern thread_local Block *g_block;
@@ -169,6 +173,16 @@ namespace emu {
 void cp_async_issue(void *smem_dst, const void *gmem_src, unsigned bytes);
 void cp_async_commit();
 void cp_async_wait(int allow_pending_groups);
+}  // namespace emu
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier.  A bulk tensor copy is queued on the block and performed -- box by box, with the
+// tensor map's swizzle and zero fill of out-of-range coordinates -- when some thread waits on the mbarrier it signals; a wait
+// whose phase can never complete (no copy queued, byte count different from expect_tx) aborts instead of spinning.
+namespace emu {
+void mbar_init(uint64_t *bar, int count);
+void mbar_expect_tx(uint64_t *bar, unsigned bytes);
+void mbar_wait(uint64_t *bar, unsigned parity);
+void tma_load(void *smem_dst, const void *tensor_map, const int *coords, int ncoords, uint64_t *bar);
 }  // namespace emu
 
 // ---- atomics (blocks run on several OS threads) -----------------------------------------------------
