@@ -3,7 +3,7 @@
 #
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_session.sh r2a'
 #
-# Stages can be switched off with SKIP="tests ncu ..." (space separated: tests smoke mb bench ab variants ncu ncufull).
+# Stages can be switched off with SKIP="tests ncu ..." (space separated: tests smoke mb bench ab sanitizer variants ncu ncufull).
 # Numbers printed under ncu are never bench values; the bench lines come from the plain runs.
 TAG=${1:-s}
 O=gpurun_out
@@ -39,6 +39,30 @@ if ! skip ab; then   # A/B of the opt-in paths against the default, same box, ba
   SMB_FUSED_LAYERNORM=1 timeout 300 python -m pytest tests/test_gpu_zz_layernorm.py -q > $O/${TAG}_pytest_ln.log 2>&1
   timeout 300 python tools/op_breakdown.py > $O/${TAG}_breakdown.log 2>&1
   timeout 900 python tools/ref_equivalent_step.py --native --steps 5 --out $O/${TAG}_ref_equivalent_step.json > $O/${TAG}_ref_equivalent_step.log 2>&1
+fi
+if ! skip sanitizer; then   # memcheck + racecheck of the opt-in kernels at small sizes (their first hardware runs)
+  cat > $O/${TAG}_san.py <<'PY'
+import os, sys, torch
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+from util import rand_scan_inputs
+from segmamba_b200 import selective_scan_cuda as ssc, causal_conv1d_cuda as cc
+from segmamba_b200.layer_norm import fused_layer_norm
+for mode in ("1", "2"):
+    os.environ["SMB_FWD_V2"] = mode; os.environ["SMB_RAGG_V2"] = "1"; os.environ["SMB_CONV_V2"] = "1"
+    for direction in (0, 1):
+        d = rand_scan_inputs(3, 2, 40, 1000, 16, 1, torch.bfloat16)
+        B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
+        o = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, direction=direction, want_hstates=True)
+        ssc.bwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], d["dout"], None, True, False, direction=direction, hstates=o[3])
+        x = torch.randn(2, 40, 1000, device="cuda").bfloat16(); w = torch.randn(40, 4, device="cuda"); b = torch.randn(40, device="cuda")
+        y = cc.causal_conv1d_fwd_ex(x, w, b, True, direction=direction)
+        cc.causal_conv1d_bwd_ex(x, w, b, y, None, True, direction=direction)
+t = torch.randn(700, 96, device="cuda").bfloat16().requires_grad_(); g = torch.rand(96, device="cuda").requires_grad_(); bb = torch.zeros(96, device="cuda").requires_grad_()
+fused_layer_norm(t, g, bb).float().sum().backward()
+torch.cuda.synchronize(); print("sanitizer workload done")
+PY
+  timeout 900 compute-sanitizer --tool memcheck python $O/${TAG}_san.py > $O/${TAG}_san_memcheck.log 2>&1
+  timeout 900 compute-sanitizer --tool racecheck python $O/${TAG}_san.py > $O/${TAG}_san_racecheck.log 2>&1
 fi
 if ! skip variants; then   # build-time tuning variants, if tools/build_variants.py was run before the call
   for lib in segmamba_b200/variants/lib_*.so; do
