@@ -505,3 +505,19 @@ def test_emu_scan_fwd_tma_layouts_and_orders(monkeypatch):
         for direction in (0, 1):
             res = tg._run_fwd_bwd(d2, direction=direction, use_hstates=True)
             tg._compare(res, tg._oracle_fwd_bwd(d, flip=bool(direction)), torch.bfloat16, True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_emu_seq_permute_into_out_and_accumulate(dtype):
+    """the `out=` / `accumulate=` form of smb_seq_permute: dst (+)= permuted src."""
+    from segmamba_b200 import causal_conv1d_cuda as cc
+    x = torch.randn(2, 12, 512).to(dtype)
+    ref = x.reshape(2, 12, 512 // 16, 16).permute(0, 1, 3, 2).flatten(-2)          # inverse permutation (mamba_simple.py:261)
+    y0 = torch.randn(2, 12, 512).to(dtype)
+    y = y0.clone()
+    got = cc.seq_permute(x, 16, inverse=True, out=y, accumulate=True)
+    assert got is y
+    assert_close(y, (y0.float() + ref.float()), 1e-6 if dtype == torch.float32 else 1e-2, "accumulate")
+    z = torch.empty_like(x)
+    cc.seq_permute(x, 16, inverse=True, out=z)
+    assert torch.equal(z, ref)
