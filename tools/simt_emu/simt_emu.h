@@ -14,7 +14,11 @@
 //     arrived -- so convergence bugs deadlock loudly ("no runnable thread") instead of computing garbage;
 //   * lanes are resumed in ascending or (SMB_EMU_REVERSE=1) descending order: a missing barrier between a
 //     shared-memory write and a cross-lane read shows up as a wrong result in one of the two orders;
-//   * shuffles from an exited lane or a lane outside the mask abort.
+//   * shuffles from an exited lane or a lane outside the mask abort;
+//   * cp.async copies are deferred until the issuing thread waits for their group, TMA bulk tensor copies until a thread waits
+//     on the mbarrier they signal (box copy with the tensor map's swizzle and zero fill; the landed bytes must equal expect_tx),
+//     so a missing wait / barrier reads NaN poison, and copies still in flight at thread exit abort;
+//   * build.py --asan adds AddressSanitizer: out-of-bounds accesses of a kernel abort with the .cu source line.
 #pragma once
 
 #ifndef SMB_EMU
