@@ -521,3 +521,28 @@ def test_emu_seq_permute_into_out_and_accumulate(dtype):
     z = torch.empty_like(x)
     cc.seq_permute(x, 16, inverse=True, out=z)
     assert torch.equal(z, ref)
+
+
+@pytest.mark.parametrize("mode", ["1", "2"], ids=["cp_async", "tma"])
+def test_emu_scan_fwd_v2_mixer_layout(monkeypatch, mode):
+    """the operand layout the mixer really produces (selective_scan_interface.py: MambaInnerFnNoOutProj): u, delta, z channel-major
+    and B, C row slices of one (R + 2N, b * l) matrix, i.e. state stride b * l > batch stride l -- the tensor maps then take the
+    batch axis before the channel / state axis."""
+    monkeypatch.setenv("SMB_FWD_V2", mode)
+    monkeypatch.setenv("SMB_RAGG_V2", "1")
+    batch, dim, L, N = 2, 40, 1000, 16
+    d = rand_scan_inputs(13, batch, dim, L, N, 1, torch.bfloat16, device="cpu")
+    hbl = lambda t: t.permute(1, 0, 2).contiguous().permute(1, 0, 2)
+    x_dblT = torch.zeros(3 + 2 * N, batch * L, dtype=torch.bfloat16)
+    x_dblT[3:3 + N] = d["B"].permute(1, 0, 2).reshape(N, batch * L)
+    x_dblT[3 + N:] = d["C"].permute(1, 0, 2).reshape(N, batch * L)
+    Bm = x_dblT[3:3 + N].view(N, batch, L).permute(1, 0, 2).unsqueeze(1)
+    Cm = x_dblT[-N:].view(N, batch, L).permute(1, 0, 2).unsqueeze(1)
+    assert Bm.stride() == (L, N * batch * L, batch * L, 1) or Bm.stride(2) == batch * L
+    d2 = dict(d)
+    for k in ("u", "delta", "z", "dout"):
+        d2[k] = hbl(d[k])
+    d2["B"], d2["C"] = Bm, Cm
+    for direction in (0, 1):
+        res = tg._run_fwd_bwd(d2, direction=direction, use_hstates=True)
+        tg._compare(res, tg._oracle_fwd_bwd(d, flip=bool(direction)), torch.bfloat16, True)
