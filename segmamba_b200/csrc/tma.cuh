@@ -76,17 +76,25 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Bounded wait: a tile lands within microseconds, so a phase that has not completed after ~2^22 polls (each try_wait itself
+// suspends for a hardware-defined interval) can only mean a mis-armed barrier (expect_tx != bytes delivered) or a faulted copy.
+// Trap instead of spinning forever: the launch then fails with an error the host sees, and the box is not held.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "SMB_MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra SMB_MBAR_DONE;\n"
-        "bra SMB_MBAR_WAIT;\n"
-        "SMB_MBAR_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
+    const unsigned addr = smem_u32(bar);
+    for (unsigned spins = 0;; ++spins) {
+        unsigned done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins > (1u << 22)) __trap();
+    }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(void *smem, const CUtensorMap *m, int c0, int c1, int c2, uint64_t *bar) {

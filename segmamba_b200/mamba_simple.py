@@ -8,6 +8,7 @@ fast path.  The decode-time ``step``, the v2/none branches and ``Block`` are out
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -16,6 +17,18 @@ import torch.nn.functional as F
 from . import causal_conv1d_cuda
 from ._lib import DIR_FORWARD, DIR_REVERSE
 from .selective_scan_interface import mamba_inner_fn_no_out_proj
+
+
+# opt-in: run the three directional passes of a mixer on separate CUDA streams (see Mamba.forward)
+DIRECTION_STREAMS = os.environ.get("SMB_DIR_STREAMS", "0") == "1"
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _SIDE_STREAMS[key]
 
 
 class Mamba(nn.Module):
@@ -112,11 +125,34 @@ class Mamba(nn.Module):
                 getattr(self, f"D{sfx}").float(), delta_bias=getattr(self, f"dt_proj{sfx}").bias.float(),
                 delta_softplus=True, direction=direction)
 
-        out = inner(xz, "", DIR_FORWARD)                                   # :217-229
-        out_b = inner(xz, "_b", DIR_REVERSE)                               # :230-242 without the flip copies
-        xz_s = _SeqPermute.apply(xz, self.nslices, False)                  # :245-247
-        out_s = inner(xz_s, "_s", DIR_FORWARD)                             # :248-260
-        out_s = _SeqPermute.apply(out_s, self.nslices, True)               # :261
+        def slice_pass():
+            xz_s = _SeqPermute.apply(xz, self.nslices, False)              # :245-247
+            return _SeqPermute.apply(inner(xz_s, "_s", DIR_FORWARD), self.nslices, True)    # :248-261
+
+        if DIRECTION_STREAMS and xz.is_cuda:
+            # The three directional passes are independent until the sum below.  At the deep stages (L = 4096 / 512) one pass
+            # cannot fill 148 SMs, so the reversed and the inter-slice pass are enqueued on two side streams (forked from and
+            # joined to the caller's stream; inside a CUDA-graph capture these become parallel branches).  Autograd replays
+            # each branch's backward on the stream its forward ran on.  Opt-in until measured (SMB_DIR_STREAMS=1).
+            cur = torch.cuda.current_stream()
+            s_b, s_s = _side_streams(xz.device)
+            s_b.wait_stream(cur)
+            s_s.wait_stream(cur)
+            xz.record_stream(s_b)
+            xz.record_stream(s_s)
+            with torch.cuda.stream(s_b):
+                out_b = inner(xz, "_b", DIR_REVERSE)
+            with torch.cuda.stream(s_s):
+                out_s = slice_pass()
+            out = inner(xz, "", DIR_FORWARD)
+            cur.wait_stream(s_b)
+            cur.wait_stream(s_s)
+            out_b.record_stream(cur)
+            out_s.record_stream(cur)
+        else:
+            out = inner(xz, "", DIR_FORWARD)                               # :217-229
+            out_b = inner(xz, "_b", DIR_REVERSE)                           # :230-242 without the flip copies
+            out_s = slice_pass()
         y = out + out_b + out_s
         return F.linear(y.permute(0, 2, 1), self.out_proj.weight, self.out_proj.bias)     # :264
 

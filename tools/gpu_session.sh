@@ -26,6 +26,8 @@ if ! skip bench; then
 fi
 if ! skip ab; then   # A/B of the opt-in paths against the default, same box, back to back
   SMB_FUSED_LAYERNORM=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_ln.json 2> $O/${TAG}_bench_ln.err
+  SMB_DIR_STREAMS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_dirstreams.json 2> $O/${TAG}_bench_dirstreams.err
+  SMB_DIR_STREAMS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --cuda-graph > $O/${TAG}_bench_dirstreams_graph.json 2> $O/${TAG}_bench_dirstreams_graph.err
   SMB_FWD_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_fwdv2.json 2> $O/${TAG}_bench_fwdv2.err
   SMB_CONV_V2=1 timeout 300 python tools/microbench.py --dtypes bf16 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_convv2.json > $O/${TAG}_mb_convv2.log 2>&1
   SMB_FWD_V2=1 SMB_RAGG_V2=1 SMB_CONV_V2=1 SMB_FUSED_LAYERNORM=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_all_optin.json 2> $O/${TAG}_bench_all_optin.err
