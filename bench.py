@@ -235,6 +235,11 @@ def main_native(args):
         # In-switch reduction (NVLS) is a bonus for a 270 MB gradient all-reduce, not a requirement; its
         # multicast set-up needs fabric-manager support that not every container exposes, so it is opt-in here.
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        if args.cuda_graph:
+            # whole-step capture with DDP inside (PyTorch CUDA-graph notes): the process group's watchdog must not poll
+            # events of a capturing stream, DDP is constructed on a side stream and runs >= 11 eager iterations before capture
+            os.environ["TORCH_NCCL_ASYNC_ERROR_HANDLING"] = "0"
+            os.environ["NCCL_ASYNC_ERROR_HANDLING"] = "0"
         _start_stall_watchdog(rank, 420.0 + 0.5 * (args.steps + args.warmup))   # if a collective stalls, say where and stop (stderr; stdout stays the JSON line)
         _log(rank, "init_process_group(nccl)")
         dist.init_process_group(backend="nccl", device_id=dev, timeout=datetime.timedelta(minutes=10))
@@ -251,7 +256,14 @@ def main_native(args):
     net = model
     if world > 1:
         _log(rank, "wrapping the model in DistributedDataParallel")
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+        if args.cuda_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
     opt = torch.optim.SGD(model.parameters(), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)   # 3_train.py:51-52
     B, P = args.batch, args.patch
     g = torch.Generator().manual_seed(42 + rank)                                                           # trainer.py:331
@@ -276,9 +288,11 @@ def main_native(args):
     if args.cuda_graph:
         from segmamba_b200.graph_step import GraphedTrainStep
         l0 = _lib.launch_count()
+        gw = 3 if world == 1 else 11                               # DDP needs 11 eager iterations before a capture
+        _log(rank, f"capturing the step in a CUDA graph ({gw} eager warm-up iterations first)")
         graphed = GraphedTrainStep(net, opt, torch.nn.functional.cross_entropy, x_dev.contiguous(memory_format=mf), y_dev,
-                                   autocast_dtype=torch.bfloat16, clip_grad_norm=12.0, warmup_iters=3)
-        graph_launches = (_lib.launch_count() - l0) // 4          # 3 warm-up steps + the captured one
+                                   autocast_dtype=torch.bfloat16, clip_grad_norm=12.0, warmup_iters=gw)
+        graph_launches = (_lib.launch_count() - l0) // (gw + 1)   # gw warm-up steps + the captured one
         eager_step = step
 
         def step(x, y):                                            # noqa: F811  (replay instead of eager launch)
