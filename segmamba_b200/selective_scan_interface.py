@@ -13,10 +13,16 @@ dB/dC come back already reduced over channels.  There is no CPU path: non-CUDA t
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import causal_conv1d_cuda, selective_scan_cuda
+
+# keep conv1d_out and delta for the backward instead of recomputing them (SMB_RECOMPUTE=1 restores the reference's
+# checkpoint_lvl=1 behaviour, ssi.py:216-219)
+KEEP_CONV_DELTA = os.environ.get("SMB_RECOMPUTE", "0") != "1"
 
 
 class SelectiveScanFn(torch.autograd.Function):
@@ -147,13 +153,18 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
                                                       direction=direction, want_out=False, want_x=False, want_hstates=True)
         ctx.delta_softplus = delta_softplus
         ctx.direction = direction
-        ctx.save_for_backward(xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst)
+        # checkpoint_lvl: the reference frees conv1d_out and delta and recomputes them in backward (ssi.py:216-219,238-241) to
+        # fit 16-32 GB parts.  With 180 GB of HBM the two (b, d_inner, l) tensors are kept instead (1.6 GB per training step
+        # of the default model at batch 2), which removes one conv1d launch and one GEMM per direction from the backward.
+        keep = (conv1d_out, delta) if KEEP_CONV_DELTA else (None, None)
+        ctx.save_for_backward(xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst, *keep)
         return out_z
 
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        (xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst) = ctx.saved_tensors
+        (xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst,
+         conv1d_out, delta) = ctx.saved_tensors
         L = xz.shape[-1]
         delta_rank = delta_proj_weight.shape[1]
         d_state = A.shape[-1]
@@ -161,11 +172,12 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         x, z = xz.chunk(2, dim=1)
         if dout.stride(-1) != 1:
             dout = dout.contiguous()
-        # recompute conv1d_out and delta (ssi.py:238-241)
-        conv1d_out = causal_conv1d_cuda.causal_conv1d_fwd_ex(x, conv1d_weight, conv1d_bias, True, direction=direction)
+        if conv1d_out is None:                          # recompute conv1d_out and delta (ssi.py:238-241)
+            conv1d_out = causal_conv1d_cuda.causal_conv1d_fwd_ex(x, conv1d_weight, conv1d_bias, True, direction=direction)
         bsz, d_inner, _ = conv1d_out.shape
         conv2 = _as_dbl(conv1d_out)
-        delta = (delta_proj_weight @ x_dblT[:delta_rank]).view(d_inner, bsz, L).permute(1, 0, 2)
+        if delta is None:
+            delta = (delta_proj_weight @ x_dblT[:delta_rank]).view(d_inner, bsz, L).permute(1, 0, 2)
         Bm = x_dblT[delta_rank:delta_rank + d_state].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
         Cm = x_dblT[-d_state:].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
         dxz = torch.empty_like(xz)                      # dx and dz are written next to each other (ssi.py:244-245)
