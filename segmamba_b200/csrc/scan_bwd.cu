@@ -770,6 +770,11 @@ static cudaError_t launch_bwd(const ScanP &p, cudaStream_t st) {
         return cudaGetLastError();
     }
     // R3 (low-memory path; also used when the caller wants out_z recomputed)
+    {   // opt-in second-generation R3 (scan_bwd_r3v2.cu): same results, fewer instructions per update
+        const char *r3v2 = getenv("SMB_R3_V2");
+        if (r3v2 && r3v2[0] == '1')
+            return scan_bwd_main_v2_dispatch(p, std::is_same<T, float>::value ? 0 : (std::is_same<T, __half>::value ? 1 : 2), N, kHasZ, st);
+    }
     const size_t sm3 = (size_t)(2 * N + 2 * kBwdWarps) * kRowPad * sizeof(float);
     SMB_SET_SMEM_ONCE((scan_bwd_main_kernel<T, N, kHasZ>), sm3);
     const int octs = ((p.dim_per_group + kBwdWarps - 1) / kBwdWarps) * p.G;

@@ -87,6 +87,8 @@ cudaError_t x_finalize_launch(const ScanP &p, int N, float *x, cudaStream_t st);
 cudaError_t scan_fwd_agg_dispatch(const ScanP &p, int dtype, int N, cudaStream_t st);
 // software-pipelined R1 (reverse aggregate) for 16-bit activations, scan_bwd_v2.cu; chosen by launch_bwd when SMB_RAGG_V2=1
 cudaError_t scan_bwd_ragg_v2_dispatch(const ScanP &p, int dtype, int N, bool has_z, cudaStream_t st);
+// second-generation R3 (main backward pass), scan_bwd_r3v2.cu; chosen by launch_bwd when SMB_R3_V2=1
+cudaError_t scan_bwd_main_v2_dispatch(const ScanP &p, int dtype, int N, bool has_z, cudaStream_t st);
 cudaError_t scan_bwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, cudaStream_t st);
 cudaError_t carry_launch(const float *P, const float *H, float *hin, float *cumP, int batch, int n_seg, int N, int dim,
                          int reverse_carry, cudaStream_t st);

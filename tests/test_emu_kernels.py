@@ -408,6 +408,41 @@ def test_emu_scan_ragg_v2_thread_orders(monkeypatch):
             tg._compare(res, tg._oracle_fwd_bwd(d, flip=bool(direction)), torch.bfloat16, True)
 
 
+# ----------------------------------------------------------------------------- second-generation R3 (SMB_R3_V2=1)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+@pytest.mark.parametrize("shape", [(2, 40, 700, 16, 1), (1, 33, 31, 16, 1), (2, 48, 600, 8, 2), (1, 64, 2304, 16, 1), (1, 7, 1021, 16, 1)],
+                         ids=lambda s: "b%d_d%d_L%d_n%d_g%d" % s)
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_emu_scan_r3_v2_vs_oracle(monkeypatch, dtype, shape, direction):
+    """scan_bwd_main2_kernel (predicated Kogge-Stone steps, folded chunk seeds, two states per barrier round, vector dB / dC
+    reductions, shared-memory dA partials): all gradients against the oracle, with and without z, ragged lengths (scalar
+    atomics path: L % 4 != 0), partial channel octets and groups."""
+    monkeypatch.setenv("SMB_R3_V2", "1")
+    batch, dim, L, N, G = shape
+    d = rand_scan_inputs(100 + L, batch, dim, L, N, G, dtype, device="cpu")
+    for has_z in (True, False):
+        res = tg._run_fwd_bwd(d, has_z=has_z, direction=direction, use_hstates=True)
+        ref = tg._oracle_fwd_bwd(d, has_z=has_z, flip=bool(direction))
+        tg._compare(res, ref, dtype, has_z)
+
+
+def test_emu_scan_r3_v2_matches_default_and_thread_orders(monkeypatch):
+    """same inputs through both R3 generations: gradients agree to fp32 round-off (same arithmetic up to the order of the
+    fp32 sums), also with the threads of a block resumed in descending / pseudo-random order (missing barrier => mismatch)."""
+    d = rand_scan_inputs(11, 2, 40, 900, 16, 1, torch.float32, device="cpu")
+    for direction in (0, 1):
+        monkeypatch.setenv("SMB_R3_V2", "0")
+        emu.emu_lib().smb_emu_set_reverse(0)
+        ref = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)
+        monkeypatch.setenv("SMB_R3_V2", "1")
+        for order in (0, 1, 5):
+            emu.emu_lib().smb_emu_set_reverse(order)
+            got = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)
+            for a, b in zip(got[4], ref[4]):
+                if a is not None and b is not None:
+                    assert_close(a, b, 2e-5, "R3 v2 vs default R3")
+
+
 # ------------------------------------------------------------------------------------------- properties and inference path
 def test_emu_scan_linearity_and_reverse_equals_flip():
     """size-independent properties: y is linear in u for fixed delta, B, C; direction=1 equals the op on flipped operands."""

@@ -144,3 +144,28 @@ def test_direction_streams_match_serial(monkeypatch):
         assert_close(res[k][0], res[0][0], 1e-5, "logits, streams vs serial")
         for g1, g0 in zip(res[k][1], res[0][1]):
             assert_close(g1, g0, 2e-2, "parameter gradient, streams vs serial")     # fp32 atomics: order-dependent rounding
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+def test_scan_r3_v2_matches_default(monkeypatch, dtype, direction):
+    """second-generation R3 (SMB_R3_V2=1, scan_bwd_r3v2.cu): every gradient equals the default R3's at a ragged small size
+    (scalar-atomic tail, partial channel octet) and at the stage-0 size (vector reductions)."""
+    from segmamba_b200 import selective_scan_cuda as ssc
+    from util import rand_scan_inputs
+    for (batch, dim, L) in ((2, 44, 5003), (2, 96, 262144)):
+        d = rand_scan_inputs(29, batch, dim, L, 16, 1, dtype)
+        B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
+        _, _, _, hst = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, direction=direction,
+                                  want_out=False, want_x=False, want_hstates=True)
+        run = lambda: ssc.bwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], d["dout"], None, True, True,
+                                 direction=direction, hstates=hst)
+        monkeypatch.setenv("SMB_R3_V2", "0")
+        ref = run()
+        monkeypatch.setenv("SMB_R3_V2", "1")
+        got = run()
+        torch.cuda.synchronize()
+        tol = 1e-2 if dtype == torch.bfloat16 else 2e-4
+        for a, b, n in zip(got, ref, ("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias", "dz", "out_z")):
+            if a is not None and b is not None:
+                assert_close(a, b, tol, n)

@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "segmamba_b200", "csrc")
 OUTD = os.path.join(ROOT, "segmamba_b200", "variants")
-SRCS = ["capi.cu", "scan_fwd.cu", "scan_fwd_v2.cu", "scan_bwd.cu", "scan_bwd_v2.cu", "conv1d.cu", "conv1d_v2.cu", "instnorm.cu", "layernorm.cu"]
+SRCS = ["capi.cu", "scan_fwd.cu", "scan_fwd_v2.cu", "scan_bwd.cu", "scan_bwd_v2.cu", "scan_bwd_r3v2.cu", "conv1d.cu", "conv1d_v2.cu", "instnorm.cu", "layernorm.cu"]
 NVFLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
            "-fvisibility=hidden", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++", "-Xptxas", "-v"]
 

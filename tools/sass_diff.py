@@ -32,9 +32,8 @@ def main():
         print("  REMOVED", k[:110])
     fam = {}
     for k in set(b) - set(a):
-        f = re.sub(r"^_ZN3smb\d+", "", k)
-        f = re.match(r"[a-z0-9_]+?_kernel", f)
-        fam[f.group(0) if f else k] = fam.get(f.group(0) if f else k, 0) + 1
+        f = re.search(r"\d+([a-z][a-z0-9_]*?_kernel)I", k) or re.search(r"\d+([a-z][a-z0-9_]*?_kernel)", k)
+        fam[f.group(1) if f else k] = fam.get(f.group(1) if f else k, 0) + 1
     for f, n in sorted(fam.items()):
         print(f"  NEW {f} x{n}")
 
