@@ -23,6 +23,9 @@ from . import causal_conv1d_cuda, selective_scan_cuda
 # keep conv1d_out and delta for the backward instead of recomputing them (SMB_RECOMPUTE=1 restores the reference's
 # checkpoint_lvl=1 behaviour, ssi.py:216-219)
 KEEP_CONV_DELTA = os.environ.get("SMB_RECOMPUTE", "0") != "1"
+# zero-pad the dt block of x_proj / dt_proj to a multiple of 8 rows so that no GEMM of the mixer has a 3- or 6-element
+# leading dimension (SMB_ALIGN_GEMMS=0 restores the reference's shapes)
+ALIGN_GEMMS = os.environ.get("SMB_ALIGN_GEMMS", "1") != "0"
 
 
 class SelectiveScanFn(torch.autograd.Function):
@@ -144,15 +147,25 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         # what conv1d_out already is in memory: x_proj / dt_proj become plain GEMMs on that view and B, C are strided
         # views of their result -- no 'b d l -> (b l) d' transpose copy (ssi.py:181) and no .contiguous() of B / C (:187-207).
         conv2 = _as_dbl(conv1d_out)                                                     # (d_inner, b*l)
-        x_dblT = x_proj_weight @ conv2                                                  # (R+2N, b*l)   = x_dbl.t()   :181
-        delta = (delta_proj_weight @ x_dblT[:delta_rank]).view(d_inner, bsz, L).permute(1, 0, 2)       # HBL          :182
-        Bm = x_dblT[delta_rank:delta_rank + d_state].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)   # (b,1,N,l) view
-        Cm = x_dblT[-d_state:].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
+        # dt_rank = ceil(d_model / 16) is 3 / 6 / 12 at the first three stages: GEMMs with a 3- or 6-element leading dimension
+        # fall back to cuBLAS's unaligned legacy kernels (cutlass_75_*_align1 in profiles/r1_launches_train_step_v3.csv, up to
+        # 0.26 ms for a 96 x 3 output).  The two small weights are therefore zero-padded so that the dt block of x_dbl has R8 =
+        # 8 / 8 / 16 rows and B, C start on 8-row boundaries; the padding rows / columns are exact zeros everywhere.
+        R8 = -(-delta_rank // 8) * 8 if ALIGN_GEMMS else delta_rank
+        if R8 != delta_rank:
+            x_proj_weight = torch.cat([x_proj_weight[:delta_rank], x_proj_weight.new_zeros(R8 - delta_rank, d_inner),
+                                       x_proj_weight[delta_rank:]], dim=0)             # (R8+2N, d_inner)
+            delta_proj_weight = torch.nn.functional.pad(delta_proj_weight, (0, R8 - delta_rank))   # (d_inner, R8)
+        x_dblT = x_proj_weight @ conv2                                                  # (R8+2N, b*l)  = x_dbl.t()   :181
+        delta = (delta_proj_weight @ x_dblT[:R8]).view(d_inner, bsz, L).permute(1, 0, 2)               # HBL          :182
+        Bm = x_dblT[R8:R8 + d_state].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)                # (b,1,N,l) view
+        Cm = x_dblT[R8 + d_state:].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
         D = D.contiguous() if D is not None else None
         _, _, out_z, hst = selective_scan_cuda.fwd_ex(conv1d_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus,
                                                       direction=direction, want_out=False, want_x=False, want_hstates=True)
         ctx.delta_softplus = delta_softplus
         ctx.direction = direction
+        ctx.delta_rank = delta_rank
         # checkpoint_lvl: the reference frees conv1d_out and delta and recomputes them in backward (ssi.py:216-219,238-241) to
         # fit 16-32 GB parts.  With 180 GB of HBM the two (b, d_inner, l) tensors are kept instead (1.6 GB per training step
         # of the default model at batch 2), which removes one conv1d launch and one GEMM per direction from the backward.
@@ -166,7 +179,7 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         (xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst,
          conv1d_out, delta) = ctx.saved_tensors
         L = xz.shape[-1]
-        delta_rank = delta_proj_weight.shape[1]
+        delta_rank, R8 = ctx.delta_rank, delta_proj_weight.shape[1]     # the saved weights carry the zero padding (see forward)
         d_state = A.shape[-1]
         direction = ctx.direction
         x, z = xz.chunk(2, dim=1)
@@ -177,23 +190,26 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         bsz, d_inner, _ = conv1d_out.shape
         conv2 = _as_dbl(conv1d_out)
         if delta is None:
-            delta = (delta_proj_weight @ x_dblT[:delta_rank]).view(d_inner, bsz, L).permute(1, 0, 2)
-        Bm = x_dblT[delta_rank:delta_rank + d_state].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
-        Cm = x_dblT[-d_state:].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
+            delta = (delta_proj_weight @ x_dblT[:R8]).view(d_inner, bsz, L).permute(1, 0, 2)
+        Bm = x_dblT[R8:R8 + d_state].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
+        Cm = x_dblT[R8 + d_state:].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
         dxz = torch.empty_like(xz)                      # dx and dz are written next to each other (ssi.py:244-245)
         dx, dz = dxz.chunk(2, dim=1)
         dconv1d_out, ddelta, dA, dB, dC, dD, ddelta_bias, dz, _ = selective_scan_cuda.bwd_ex(
             conv1d_out, delta, A, Bm, Cm, D, z, delta_bias, dout, dz, ctx.delta_softplus, False,
             direction=direction, hstates=hst)
-        dx_dblT = torch.empty_like(x_dblT)                                                                      # (R+2N, b*l)
-        dx_dblT[delta_rank:delta_rank + d_state].view(d_state, bsz, L).copy_(dB.squeeze(1).permute(1, 0, 2))   # :255-262
-        dx_dblT[-d_state:].view(d_state, bsz, L).copy_(dC.squeeze(1).permute(1, 0, 2))                          # :264-271
+        dx_dblT = torch.empty_like(x_dblT)                                                                      # (R8+2N, b*l)
+        dx_dblT[R8:R8 + d_state].view(d_state, bsz, L).copy_(dB.squeeze(1).permute(1, 0, 2))                    # :255-262
+        dx_dblT[R8 + d_state:].view(d_state, bsz, L).copy_(dC.squeeze(1).permute(1, 0, 2))                      # :264-271
         ddelta2 = _as_dbl(ddelta)                                                                               # :272
-        ddelta_proj_weight = ddelta2 @ x_dblT[:delta_rank].t()                                                  # :273
-        dx_dblT[:delta_rank] = delta_proj_weight.t() @ ddelta2                                                  # :274
+        ddelta_proj_weight = ddelta2 @ x_dblT[:R8].t()                                                          # :273
+        dx_dblT[:R8] = delta_proj_weight.t() @ ddelta2               # rows delta_rank..R8 come out as exact zeros  :274
         dconv2 = _as_dbl(dconv1d_out)                                                                           # :275
         dx_proj_weight = dx_dblT @ conv2.t()                                                                    # :276
         dconv2 = torch.addmm(dconv2, x_proj_weight.t(), dx_dblT)                                                # :277
+        if R8 != delta_rank:                                          # gradients of the un-padded parameters
+            ddelta_proj_weight = ddelta_proj_weight[:, :delta_rank]
+            dx_proj_weight = torch.cat([dx_proj_weight[:delta_rank], dx_proj_weight[R8:]], dim=0)
         dconv1d_out = dconv2.view(d_inner, bsz, L).permute(1, 0, 2)                                             # :278
         dx, dconv1d_weight, dconv1d_bias = causal_conv1d_cuda.causal_conv1d_bwd_ex(
             x, conv1d_weight, conv1d_bias, dconv1d_out, dx, True, direction=direction)                          # :281-283
