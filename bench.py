@@ -235,6 +235,7 @@ def main_native(args):
         # In-switch reduction (NVLS) is a bonus for a 270 MB gradient all-reduce, not a requirement; its
         # multicast set-up needs fabric-manager support that not every container exposes, so it is opt-in here.
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        os.environ.setdefault("NCCL_MNNVL_ENABLE", "0")   # one box: never wait for a multi-node NVLink fabric (IMEX) that is not there
         if args.cuda_graph:
             # whole-step capture with DDP inside (PyTorch CUDA-graph notes): the process group's watchdog must not poll
             # events of a capturing stream, DDP is constructed on a side stream and runs >= 11 eager iterations before capture
