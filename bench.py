@@ -41,6 +41,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--channels-last", action="store_true", help="channels_last_3d activations for the conv stack")
     ap.add_argument("--cuda-graph", action="store_true", help="capture the whole step (fwd+bwd+clip+SGD) in one CUDA graph")
+    ap.add_argument("--bf16-params", action="store_true",
+                    help="bf16 matmul / convolution parameters with fp32 masters in the optimizer (segmamba_b200/master_weights.py): "
+                         "same arithmetic as autocast, two multi-tensor copies per step instead of ~400 cast kernels")
     ap.add_argument("--cpu-sample", type=int, default=32, help="edge of the cubic crop the CPU arm runs per step")
     return ap.parse_args()
 
@@ -254,6 +257,10 @@ def main_native(args):
     if args.channels_last:
         model = model.to(memory_format=torch.channels_last_3d)
     model.train()
+    mw = None
+    if args.bf16_params:
+        from segmamba_b200.master_weights import MasterWeights
+        mw = MasterWeights(model)                                  # before DDP: the gradient all-reduce then moves bf16
     net = model
     if world > 1:
         _log(rank, "wrapping the model in DistributedDataParallel")
@@ -265,7 +272,8 @@ def main_native(args):
             torch.cuda.current_stream().wait_stream(side)
         else:
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)
-    opt = torch.optim.SGD(model.parameters(), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)   # 3_train.py:51-52
+    opt_params = mw.optimizer_parameters() if mw is not None else list(model.parameters())
+    opt = torch.optim.SGD(opt_params, lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)             # 3_train.py:51-52
     B, P = args.batch, args.patch
     g = torch.Generator().manual_seed(42 + rank)                                                           # trainer.py:331
     x_host = torch.rand(B, 4, P, P, P, generator=g).pin_memory()
@@ -277,12 +285,18 @@ def main_native(args):
 
     def step(x, y):
         opt.zero_grad(set_to_none=True)
+        if mw is not None:
+            mw.zero_grad()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = net(x.contiguous(memory_format=mf))
             loss = torch.nn.functional.cross_entropy(logits.float(), y)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 12.0)                                           # trainer.py:464
+        if mw is not None:
+            mw.grads_to_master()
+        torch.nn.utils.clip_grad_norm_(opt_params, 12.0)                                                   # trainer.py:464
         opt.step()
+        if mw is not None:
+            mw.master_to_model()
         return loss
 
     graphed = None
@@ -292,7 +306,7 @@ def main_native(args):
         gw = 3 if world == 1 else 11                               # DDP needs 11 eager iterations before a capture
         _log(rank, f"capturing the step in a CUDA graph ({gw} eager warm-up iterations first)")
         graphed = GraphedTrainStep(net, opt, torch.nn.functional.cross_entropy, x_dev.contiguous(memory_format=mf), y_dev,
-                                   autocast_dtype=torch.bfloat16, clip_grad_norm=12.0, warmup_iters=gw)
+                                   autocast_dtype=torch.bfloat16, clip_grad_norm=12.0, warmup_iters=gw, master_weights=mw)
         graph_launches = (_lib.launch_count() - l0) // (gw + 1)   # gw warm-up steps + the captured one
         eager_step = step
 
@@ -415,7 +429,7 @@ def main_native(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2: one step touches > 10 GB of activations (126 MB L2)",
-                       "channels_last_3d": True, "cuda_graph": bool(args.cuda_graph)},
+                       "channels_last_3d": True, "cuda_graph": bool(args.cuda_graph), "bf16_params": bool(args.bf16_params)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
             "roofline_scan_bwd": roof_bwd,

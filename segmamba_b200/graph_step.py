@@ -27,12 +27,14 @@ class GraphedTrainStep:
 
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, loss_fn: Callable, x_example: torch.Tensor,
                  y_example: torch.Tensor, autocast_dtype: torch.dtype | None = torch.bfloat16, clip_grad_norm: float | None = 12.0,
-                 warmup_iters: int = 3):
+                 warmup_iters: int = 3, master_weights=None):
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
         self.autocast_dtype, self.clip = autocast_dtype, clip_grad_norm
         self.static_x = x_example.clone()
         self.static_y = y_example.clone()
-        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.master_weights = master_weights                  # optional MasterWeights (bf16 parameters, fp32 masters)
+        self.params = (master_weights.optimizer_parameters() if master_weights is not None
+                       else [p for p in model.parameters() if p.requires_grad])
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -41,20 +43,29 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        self._zero()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._eager_step(zero=False)
 
+    def _zero(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        if self.master_weights is not None:
+            self.master_weights.zero_grad()
+
     def _eager_step(self, zero: bool = True):
         if zero:
-            self.optimizer.zero_grad(set_to_none=True)
+            self._zero()
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             logits = self.model(self.static_x)
             loss = self.loss_fn(logits.float(), self.static_y)
         loss.backward()
+        if self.master_weights is not None:
+            self.master_weights.grads_to_master()
         if self.clip is not None:
             torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
         self.optimizer.step()
+        if self.master_weights is not None:
+            self.master_weights.master_to_model()
         return loss.detach()
 
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

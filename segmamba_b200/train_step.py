@@ -74,29 +74,40 @@ class TrainStep:
     autocast_dtype torch.bfloat16 (default), torch.float16 (then a GradScaler is created unless one is passed), or None.
     clip_grad_norm 12, as trainer.py:464,469; None disables.
     scheduler      anything with ``step()``; called after the optimiser step, as trainer.py:476-477.
+    master_weights optional ``MasterWeights(model)`` (segmamba_b200/master_weights.py): the model's matmul / convolution
+                   parameters live in the autocast dtype, ``optimizer`` must have been built on
+                   ``master_weights.optimizer_parameters()``; same arithmetic, two multi-tensor copies per step instead of one
+                   cast kernel per weight and per gradient.
     """
 
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, loss_fn: Callable,
                  autocast_dtype: torch.dtype | None = torch.bfloat16, grad_scaler=None, clip_grad_norm: float | None = 12.0,
-                 scheduler=None):
+                 scheduler=None, master_weights=None):
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
         self.autocast_dtype, self.clip, self.scheduler = autocast_dtype, clip_grad_norm, scheduler
         if grad_scaler is None and autocast_dtype is torch.float16:
             grad_scaler = torch.amp.GradScaler()
         self.grad_scaler = grad_scaler
         self.global_step = 0
-        self._params = [p for p in model.parameters() if p.requires_grad]
+        self.master_weights = master_weights
+        self._model_params = [p for p in model.parameters() if p.requires_grad]
+        self._params = master_weights.optimizer_parameters() if master_weights is not None else self._model_params
 
     def __call__(self, image: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
         self.global_step += 1
         self.model.train()
         for p in self._params:                                   # trainer.py:444 (grad = None, not zeros)
             p.grad = None
+        for p in self._model_params:
+            p.grad = None
         with torch.autocast(image.device.type, dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             logits = self.model(image)
             loss = self.loss_fn(logits.float(), label)
+        mw = self.master_weights
         if self.grad_scaler is not None:
             self.grad_scaler.scale(loss).backward()
+            if mw is not None:
+                mw.grads_to_master()
             self.grad_scaler.unscale_(self.optimizer)
             if self.clip is not None:
                 torch.nn.utils.clip_grad_norm_(self._params, self.clip)
@@ -104,9 +115,13 @@ class TrainStep:
             self.grad_scaler.update()
         else:
             loss.backward()
+            if mw is not None:
+                mw.grads_to_master()
             if self.clip is not None:
                 torch.nn.utils.clip_grad_norm_(self._params, self.clip)
             self.optimizer.step()
+        if mw is not None:
+            mw.master_to_model()
         if self.scheduler is not None:
             self.scheduler.step()
         return loss.detach()
@@ -116,7 +131,8 @@ class TrainStep:
         module = self.model.module if hasattr(self.model, "module") else self.model
         return {
             "format": "segmamba_b200.train_step/1",
-            "model": module.state_dict(),                         # the reference's 291 keys: loadable by 4_predict.py:52-53
+            # the reference's 291 keys in fp32: loadable by 4_predict.py:52-53
+            "model": self.master_weights.state_dict() if self.master_weights is not None else module.state_dict(),
             "optimizer": self.optimizer.state_dict(),
             "scheduler": self.scheduler.state_dict() if self.scheduler is not None and hasattr(self.scheduler, "state_dict") else None,
             "grad_scaler": self.grad_scaler.state_dict() if self.grad_scaler is not None else None,
@@ -127,7 +143,10 @@ class TrainStep:
         if state.get("format") != "segmamba_b200.train_step/1":
             raise ValueError(f"not a train_step checkpoint (format={state.get('format')!r})")
         module = self.model.module if hasattr(self.model, "module") else self.model
-        module.load_state_dict(state["model"], strict=True)
+        if self.master_weights is not None:
+            self.master_weights.load_state_dict(state["model"], strict=True)
+        else:
+            module.load_state_dict(state["model"], strict=True)
         self.optimizer.load_state_dict(state["optimizer"])
         if self.scheduler is not None and state.get("scheduler") is not None:
             self.scheduler.load_state_dict(state["scheduler"])

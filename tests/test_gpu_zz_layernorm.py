@@ -169,3 +169,33 @@ def test_scan_r3_v2_matches_default(monkeypatch, dtype, direction):
         for a, b, n in zip(got, ref, ("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias", "dz", "out_z")):
             if a is not None and b is not None:
                 assert_close(a, b, tol, n)
+
+
+def test_master_weights_step_matches_autocast_step():
+    """bf16 parameters + fp32 masters (segmamba_b200/master_weights.py) on the real model: the same losses and fp32 weights as
+    the plain autocast step over three iterations, up to the run-to-run noise of the fp32 atomics (CPU twin of this test is
+    bit-exact, tests/test_train_step.py)."""
+    import copy
+    import golden_inputs as gi
+    from segmamba_b200.master_weights import MasterWeights
+    from segmamba_b200.segmamba import SegMamba
+    from segmamba_b200.train_step import TrainStep
+    c = gi.MODEL_CASE
+    torch.manual_seed(7)
+    ref_model = SegMamba(in_chans=4, out_chans=4, depths=c["depths"], feat_size=c["feat_size"], hidden_size=c["hidden_size"]).cuda()
+    model = copy.deepcopy(ref_model)
+    mk = lambda params: torch.optim.SGD(params, lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    ref = TrainStep(ref_model, mk(ref_model.parameters()), torch.nn.CrossEntropyLoss())
+    mw = MasterWeights(model)
+    assert len(mw.converted_names()) > 100 and model.vit.stages[0][0].mamba.A_log.dtype == torch.float32
+    step = TrainStep(model, mk(mw.optimizer_parameters()), torch.nn.CrossEntropyLoss(), master_weights=mw)
+    g = torch.Generator().manual_seed(1)
+    for i in range(3):
+        x = torch.rand(2, 4, 32, 32, 32, generator=g).cuda()
+        y = torch.randint(0, 4, (2, 32, 32, 32), generator=g).cuda()
+        la, lb = float(ref(x, y)), float(step(x, y))
+        assert abs(la - lb) <= 2e-3 * abs(la), (i, la, lb)
+    sd = mw.state_dict()
+    for k, v in ref_model.state_dict().items():
+        assert sd[k].dtype == v.dtype
+        assert_close(sd[k], v, 2e-2, k)

@@ -111,3 +111,47 @@ def test_ddp_two_ranks_gloo_matches_single_process(tmp_path):
         np.testing.assert_array_equal(ret[0][k], ret[1][k])      # replicas stay identical
     saved = torch.load(ckpt, weights_only=True)
     assert set(saved["model"].keys()) == set(model.state_dict().keys())
+
+
+def _toy_with_norm():
+    torch.manual_seed(11)
+    return torch.nn.Sequential(torch.nn.Conv3d(2, 8, 3, padding=1), torch.nn.GroupNorm(2, 8), torch.nn.ReLU(),
+                               torch.nn.ConvTranspose3d(8, 8, 2, 2), torch.nn.Conv3d(8, 3, 1))
+
+
+def test_master_weights_step_equals_autocast_step(tmp_path):
+    """bf16 parameters + fp32 masters (MasterWeights) against the plain autocast step on CPU: the low-precision parameters hold
+    exactly the values autocast's casts produce, so losses and fp32 weights agree bit for bit over several steps; parameters
+    outside the matmul modules (here the GroupNorm affine) stay fp32 and are their own masters; checkpoints carry fp32."""
+    from segmamba_b200.master_weights import MasterWeights
+    g = torch.Generator().manual_seed(3)
+    xs = torch.rand(5, 2, 2, 6, 6, 6, generator=g)
+    ys = torch.randint(0, 3, (5, 2, 12, 12, 12), generator=g)
+    ref_model = _toy_with_norm()
+    ref = TrainStep(ref_model, reference_optimizer(ref_model), torch.nn.CrossEntropyLoss(), autocast_dtype=torch.bfloat16)
+    model = _toy_with_norm()
+    mw = MasterWeights(model)
+    assert set(mw.converted_names()) == {"0.weight", "0.bias", "3.weight", "3.bias", "4.weight", "4.bias"}
+    assert model[0].weight.dtype == torch.bfloat16 and model[1].weight.dtype == torch.float32
+    opt = torch.optim.SGD(mw.optimizer_parameters(), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    step = TrainStep(model, opt, torch.nn.CrossEntropyLoss(), autocast_dtype=torch.bfloat16, master_weights=mw)
+    for i in range(4):
+        la, lb = float(ref(xs[i], ys[i])), float(step(xs[i], ys[i]))
+        assert la == lb, (i, la, lb)
+    sd = mw.state_dict()
+    for k, v in ref_model.state_dict().items():
+        assert sd[k].dtype == v.dtype
+        np.testing.assert_array_equal(sd[k].numpy(), v.numpy())
+        if k in mw.converted_names():                            # the model holds the rounded masters
+            np.testing.assert_array_equal(model.state_dict()[k].float().numpy(), v.to(torch.bfloat16).float().numpy())
+    # resume: a fresh pair restored from the checkpoint continues identically
+    path = str(tmp_path / "mw.pt")
+    save_checkpoint(path, step)
+    model2 = _toy_with_norm()
+    mw2 = MasterWeights(model2)
+    opt2 = torch.optim.SGD(mw2.optimizer_parameters(), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    step2 = TrainStep(model2, opt2, torch.nn.CrossEntropyLoss(), autocast_dtype=torch.bfloat16, master_weights=mw2)
+    assert load_checkpoint(path, step2) == 4
+    assert float(ref(xs[4], ys[4])) == float(step2(xs[4], ys[4]))
+    for k, v in ref_model.state_dict().items():
+        np.testing.assert_array_equal(mw2.state_dict()[k].numpy(), v.numpy())
