@@ -90,4 +90,6 @@ if ! skip ncufull; then  # one full capture of the scan kernels (stage 0, traini
   ncu -i $O/${TAG}_scan_full.ncu-rep --page raw --csv > $O/${TAG}_scan_raw.csv 2>/dev/null
   python tools/ncu_raw_summary.py $O/${TAG}_scan_raw.csv > $O/${TAG}_scan_summary.txt 2>&1
 fi
+python tools/session_report.py $TAG $O > $O/${TAG}_report.txt 2>&1
+cat $O/${TAG}_report.txt | cut -c1-250
 ls -la $O | tail -40
