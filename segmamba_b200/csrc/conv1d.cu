@@ -241,6 +241,13 @@ static cudaError_t permute_launch_t(const void *src, void *dst, int64_t src_rs, 
 
 cudaError_t seq_permute_dispatch(const void *src, void *dst, int64_t src_rs, int64_t dst_rs, int rows, int L, int ns,
                                  int inverse, int accumulate, int dtype, cudaStream_t st) {
+    {   // opt-in 4-byte-access kernel for 16-bit activations (read per call: a tuning switch, not an API)
+        const char *v2 = getenv("SMB_PERMUTE_V2");
+        if (dtype != 0 && v2 && v2[0] == '1') {
+            const cudaError_t e = seq_permute_v2_dispatch(src, dst, src_rs, dst_rs, rows, L, ns, inverse, accumulate, dtype, st);
+            if (e != cudaErrorNotSupported) return e;
+        }
+    }
     switch (dtype) {
         case 0: return permute_launch_t<float>(src, dst, src_rs, dst_rs, rows, L, ns, inverse, accumulate, st);
         case 1: return permute_launch_t<__half>(src, dst, src_rs, dst_rs, rows, L, ns, inverse, accumulate, st);

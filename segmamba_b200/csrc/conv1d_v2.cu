@@ -4,6 +4,8 @@
 // 93 % (profiles/r1_microbench_final.json); 16 positions give the 16-bit types the same bytes in flight per thread.
 #include "conv_internal.h"
 
+#include <cstdint>
+
 namespace smb {
 
 constexpr int kConv2Threads = 128;
@@ -176,6 +178,79 @@ static cudaError_t conv2_launch_t(const ConvP &p, bool bwd, cudaStream_t st) {
     else conv1d_bwd16_kernel<T><<<grid, kConv2Threads, 0, st>>>(p);
     count_launch();
     return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// inter-slice permutation for 16-bit activations with 4-byte accesses (opt-in: SMB_PERMUTE_V2=1).
+// The default kernel (conv1d.cu) moves one 2-byte element per thread and access: a warp touches 64 bytes per row segment and
+// reaches 2.9 TB/s on the stage-0 tensor (profiles/r1_op_breakdown_final.txt).  Here a CTA transposes a 64 x 64 tile held as
+// 64 x 32 words: every global access is a 128-byte row segment of 32 element pairs; the pair that leaves along the
+// destination row is assembled from the same half of two vertically adjacent words (one PRMT).
+// Requires even n_src_rows / n_src_cols and 4-byte aligned rows; the dispatcher falls back to the default kernel otherwise.
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ unsigned add_pair(unsigned a, unsigned b);
+template <> __device__ __forceinline__ unsigned add_pair<__nv_bfloat16>(unsigned a, unsigned b) {
+    const float lo = __uint_as_float(a << 16) + __uint_as_float(b << 16);
+    const float hi = __uint_as_float(a & 0xffff0000u) + __uint_as_float(b & 0xffff0000u);
+    const __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const unsigned *>(&r);
+}
+template <> __device__ __forceinline__ unsigned add_pair<__half>(unsigned a, unsigned b) {
+    const float2 fa = __half22float2(*reinterpret_cast<const __half2 *>(&a)), fb = __half22float2(*reinterpret_cast<const __half2 *>(&b));
+    const __half2 r = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+    return *reinterpret_cast<const unsigned *>(&r);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) seq_permute2_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t src_rs,
+                                                           int64_t dst_rs, int n_src_rows, int n_src_cols, int accumulate) {
+    __shared__ unsigned tile[64][33];                      // tile[r][w]: elements (r, 2w) and (r, 2w + 1) of the source tile
+    const int row = blockIdx.z;
+    const T *s = src + (int64_t)row * src_rs;
+    T *o = dst + (int64_t)row * dst_rs;
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = r0 + ty + 8 * k, c = c0 + 2 * tx;
+        unsigned w = 0u;
+        if (r < n_src_rows && c < n_src_cols) w = *reinterpret_cast<const unsigned *>(s + (int64_t)r * n_src_cols + c);
+        tile[ty + 8 * k][tx] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int cl = ty + 8 * k;                          // destination row inside the tile = source column
+        const int c = c0 + cl, r = r0 + 2 * tx;             // dst[c][r], dst[c][r + 1]
+        if (r < n_src_rows && c < n_src_cols) {
+            const unsigned w0 = tile[2 * tx][cl >> 1], w1 = tile[2 * tx + 1][cl >> 1];
+            unsigned v = (cl & 1) ? ((w0 >> 16) | (w1 & 0xffff0000u)) : ((w0 & 0xffffu) | (w1 << 16));
+            unsigned *q = reinterpret_cast<unsigned *>(o + (int64_t)c * n_src_rows + r);
+            if (accumulate) v = add_pair<T>(v, *q);
+            *q = v;
+        }
+    }
+}
+
+template <typename T>
+static cudaError_t permute2_launch_t(const void *src, void *dst, int64_t src_rs, int64_t dst_rs, int rows, int nr, int nc,
+                                     int accumulate, cudaStream_t st) {
+    dim3 grid((nc + 63) / 64, (nr + 63) / 64, rows);
+    seq_permute2_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T *>(src), reinterpret_cast<T *>(dst), src_rs, dst_rs, nr, nc,
+                                                 accumulate); count_launch();
+    return cudaGetLastError();
+}
+
+// returns cudaErrorNotSupported when the shape / alignment does not allow 4-byte accesses (caller then uses the default kernel)
+cudaError_t seq_permute_v2_dispatch(const void *src, void *dst, int64_t src_rs, int64_t dst_rs, int rows, int L, int ns, int inverse,
+                                    int accumulate, int dtype, cudaStream_t st) {
+    const int Lp = L / ns;
+    const int nr = inverse ? Lp : ns, nc = inverse ? ns : Lp;
+    if (dtype == 0 || (nr & 1) || (nc & 1) || (src_rs & 1) || (dst_rs & 1) ||
+        ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3))
+        return cudaErrorNotSupported;
+    if (dtype == 1) return permute2_launch_t<__half>(src, dst, src_rs, dst_rs, rows, nr, nc, accumulate, st);
+    return permute2_launch_t<__nv_bfloat16>(src, dst, src_rs, dst_rs, rows, nr, nc, accumulate, st);
 }
 
 cudaError_t conv1d_v2_dispatch(const ConvP &p, int dtype, bool bwd, cudaStream_t st) {

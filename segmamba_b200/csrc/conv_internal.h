@@ -18,6 +18,9 @@ struct ConvP {
 cudaError_t conv1d_dispatch(const ConvP &p, int dtype, bool bwd, cudaStream_t st);
 // 16 positions per thread for 16-bit activations, conv1d_v2.cu; chosen by conv1d_dispatch when SMB_CONV_V2=1
 cudaError_t conv1d_v2_dispatch(const ConvP &p, int dtype, bool bwd, cudaStream_t st);
+// 4-byte-access variant for 16-bit activations (conv1d_v2.cu); cudaErrorNotSupported = shape / alignment not eligible
+cudaError_t seq_permute_v2_dispatch(const void *src, void *dst, int64_t src_rs, int64_t dst_rs, int rows, int L, int ns, int inverse,
+                                    int accumulate, int dtype, cudaStream_t st);
 cudaError_t seq_permute_dispatch(const void *src, void *dst, int64_t src_rs, int64_t dst_rs, int rows, int L, int ns,
                                  int inverse, int accumulate, int dtype, cudaStream_t st);
 

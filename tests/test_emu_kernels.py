@@ -604,3 +604,29 @@ def test_emu_scan_fwd_v2_mixer_layout(monkeypatch, mode):
     for direction in (0, 1):
         res = tg._run_fwd_bwd(d2, direction=direction, use_hstates=True)
         tg._compare(res, tg._oracle_fwd_bwd(d, flip=bool(direction)), torch.bfloat16, True)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("L,ns", [(512, 16), (4096, 64), (600, 6), (1000, 10), (96, 8), (510, 5)], ids=lambda v: str(v))
+def test_emu_seq_permute_v2(monkeypatch, dtype, L, ns):
+    """4-byte-access permutation kernel (SMB_PERMUTE_V2=1): bit-identical to the default kernel in both directions, on strided
+    (channel-major) views, with out= / accumulate=; odd shapes fall back to the default kernel."""
+    from segmamba_b200 import causal_conv1d_cuda as cc
+    torch.manual_seed(L + ns)
+    base = torch.randn(12, 2, L).to(dtype)
+    x = base.permute(1, 0, 2)                                  # (batch, dim, L) view with the mixer's channel-major strides
+    y0 = torch.randn(2, 12, L).to(dtype)
+    res = {}
+    for v2 in ("0", "1"):
+        monkeypatch.setenv("SMB_PERMUTE_V2", v2)
+        for order in (0, 3):
+            emu.emu_lib().smb_emu_set_reverse(order)
+            f = cc.seq_permute(x, ns)
+            b = cc.seq_permute(f, ns, inverse=True)
+            acc = cc.seq_permute(x, ns, inverse=True, out=y0.clone(), accumulate=True)
+            res[(v2, order)] = (f, b, acc)
+    ref = x.reshape(2, 12, ns, L // ns).transpose(-1, -2).flatten(-2)              # mamba_simple.py:245-247
+    for key, (f, b, acc) in res.items():
+        assert torch.equal(f, ref), key
+        assert torch.equal(b, x), key
+        assert torch.equal(acc, res[("0", 0)][2]), key

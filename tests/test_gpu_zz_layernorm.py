@@ -201,3 +201,18 @@ def test_master_weights_step_matches_autocast_step():
     for k, v in ref_model.state_dict().items():
         assert sd[k].dtype == v.dtype
         assert_close(sd[k], v, 2e-2, k)
+
+
+@pytest.mark.parametrize("rows,L,ns", [(384, 262144, 64), (768, 32768, 32), (3072, 512, 8)], ids=lambda v: str(v))
+def test_seq_permute_v2_matches_default(monkeypatch, rows, L, ns):
+    """4-byte-access permutation kernel (SMB_PERMUTE_V2=1) at the model's shapes: bit-identical to the default kernel."""
+    from segmamba_b200 import causal_conv1d_cuda as cc
+    torch.manual_seed(rows)
+    x = torch.randn(rows // 2, 2, L, device="cuda").bfloat16().permute(1, 0, 2)       # channel-major view, as in the mixer
+    out = {}
+    for v2 in ("0", "1"):
+        monkeypatch.setenv("SMB_PERMUTE_V2", v2)
+        f = cc.seq_permute(x, ns)
+        out[v2] = (f, cc.seq_permute(f, ns, inverse=True))
+    torch.cuda.synchronize()
+    assert torch.equal(out["1"][0], out["0"][0]) and torch.equal(out["1"][1], out["0"][1]) and torch.equal(out["1"][1], x)

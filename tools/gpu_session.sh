@@ -34,6 +34,7 @@ if ! skip ab; then   # A/B of the opt-in paths against the default, same box, ba
   SMB_FWD_V2=1 SMB_RAGG_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_fwdv2_raggv2.json 2> $O/${TAG}_bench_fwdv2_raggv2.err
   timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --bf16-params > $O/${TAG}_bench_bf16params.json 2> $O/${TAG}_bench_bf16params.err
   SMB_PAD_CIN=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_padcin.json 2> $O/${TAG}_bench_padcin.err
+  SMB_PERMUTE_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_permutev2.json 2> $O/${TAG}_bench_permutev2.err
   SMB_R3_V2=1 timeout 300 python tools/microbench.py --dtypes bf16,f32 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_r3v2.json > $O/${TAG}_mb_r3v2.log 2>&1
   SMB_R3_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_r3v2.json 2> $O/${TAG}_bench_r3v2.err
   SMB_RAGG_V2=1 timeout 300 python tools/microbench.py --dtypes bf16 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_raggv2.json > $O/${TAG}_mb_raggv2.log 2>&1
@@ -54,7 +55,7 @@ from util import rand_scan_inputs
 from segmamba_b200 import selective_scan_cuda as ssc, causal_conv1d_cuda as cc
 from segmamba_b200.layer_norm import fused_layer_norm
 for mode in ("1", "2"):
-    os.environ["SMB_FWD_V2"] = mode; os.environ["SMB_RAGG_V2"] = "1"; os.environ["SMB_CONV_V2"] = "1"; os.environ["SMB_R3_V2"] = "1"
+    os.environ["SMB_FWD_V2"] = mode; os.environ["SMB_RAGG_V2"] = "1"; os.environ["SMB_CONV_V2"] = "1"; os.environ["SMB_R3_V2"] = "1"; os.environ["SMB_PERMUTE_V2"] = "1"
     for direction in (0, 1):
         d = rand_scan_inputs(3, 2, 40, 1000, 16, 1, torch.bfloat16)
         B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
