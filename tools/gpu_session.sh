@@ -64,6 +64,7 @@ for mode in ("1", "2"):
         x = torch.randn(2, 40, 1000, device="cuda").bfloat16(); w = torch.randn(40, 4, device="cuda"); b = torch.randn(40, device="cuda")
         y = cc.causal_conv1d_fwd_ex(x, w, b, True, direction=direction)
         cc.causal_conv1d_bwd_ex(x, w, b, y, None, True, direction=direction)
+        cc.seq_permute(cc.seq_permute(x, 10), 10, inverse=True)
 t = torch.randn(700, 96, device="cuda").bfloat16().requires_grad_(); g = torch.rand(96, device="cuda").requires_grad_(); bb = torch.zeros(96, device="cuda").requires_grad_()
 fused_layer_norm(t, g, bb).float().sum().backward()
 torch.cuda.synchronize(); print("sanitizer workload done")
