@@ -253,6 +253,8 @@ def main_native(args):
 
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
+    if os.environ.get("SMB_CUDNN_BENCH_LIMIT"):                   # A/B knob: how many cuDNN plans the autotuner times (0 = all; torch default 10)
+        torch.backends.cudnn.benchmark_limit = int(os.environ["SMB_CUDNN_BENCH_LIMIT"])
     model = SegMamba(in_chans=4, out_chans=4, depths=[2, 2, 2, 2], feat_size=[48, 96, 192, 384]).to(dev)
     if args.channels_last:
         model = model.to(memory_format=torch.channels_last_3d)

@@ -34,6 +34,7 @@ if ! skip ab; then   # A/B of the opt-in paths against the default, same box, ba
   SMB_FWD_V2=1 SMB_RAGG_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_fwdv2_raggv2.json 2> $O/${TAG}_bench_fwdv2_raggv2.err
   timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --bf16-params > $O/${TAG}_bench_bf16params.json 2> $O/${TAG}_bench_bf16params.err
   SMB_PAD_CIN=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_padcin.json 2> $O/${TAG}_bench_padcin.err
+  SMB_CUDNN_BENCH_LIMIT=0 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_cudnnall.json 2> $O/${TAG}_bench_cudnnall.err
   SMB_PERMUTE_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_permutev2.json 2> $O/${TAG}_bench_permutev2.err
   SMB_R3_V2=1 timeout 300 python tools/microbench.py --dtypes bf16,f32 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_r3v2.json > $O/${TAG}_mb_r3v2.log 2>&1
   SMB_R3_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_bench_r3v2.json 2> $O/${TAG}_bench_r3v2.err
