@@ -40,6 +40,18 @@ __device__ __forceinline__ float act_grad(float v, int act, float slope) {
     return 1.f;
 }
 
+// Build-time knob (tools/build_variants.py in_rev): the apply passes walk their row range from the top down.  The statistics pass
+// that precedes them streams the same range bottom-up, so what is still in the 126 MB L2 when it ends is the TOP of every CTA's
+// range; reading that first turns part of the second read of a > L2 tensor into L2 hits.  Default off (unmeasured).
+#ifndef SMB_IN_APPLY_REVERSE
+#define SMB_IN_APPLY_REVERSE 0
+#endif
+#if SMB_IN_APPLY_REVERSE
+#define SMB_APPLY_ROW(m, row) ((m).row_lo + (m).row_hi - 1 - (row))
+#else
+#define SMB_APPLY_ROW(m, row) (row)
+#endif
+
 struct RowMap {
     int cv, r, RB;
     int64_t row_lo, row_hi;
@@ -216,8 +228,9 @@ __global__ void __launch_bounds__(kNormThreads, SMB_IN_FWD_MINB) in_apply_fwd_ke
         for (int k = 0; k < U; ++k) {
             const int64_t row = row0 + (int64_t)k * m.RB;
             if (row < m.row_hi) {
-                loadv<T, V>(x + row * C + m.cv * V, a[k]);
-                if (MODE2) loadv<T, V>(x2 + row * C + m.cv * V, b2[k]);
+                const int64_t ar = SMB_APPLY_ROW(m, row);
+                loadv<T, V>(x + ar * C + m.cv * V, a[k]);
+                if (MODE2) loadv<T, V>(x2 + ar * C + m.cv * V, b2[k]);
             }
         }
 #pragma unroll
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(kNormThreads, SMB_IN_FWD_MINB) in_apply_fwd_ke
                     if (MODE2) t += (b2[k][v] - mu2[v]) * rs2[v];
                     o[v] = act_fwd(t, p.act, p.slope);
                 }
-                storev<T, V>(y + row * C + m.cv * V, o);
+                storev<T, V>(y + SMB_APPLY_ROW(m, row) * C + m.cv * V, o);
             }
         }
     }
@@ -374,9 +387,10 @@ __global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 :
         for (int k = 0; k < U; ++k) {
             const int64_t row = row0 + (int64_t)k * m.RB;
             if (row < m.row_hi) {
-                loadv<T, V>(x + row * C + m.cv * V, a[k]);
-                loadv<T, V>(dy + row * C + m.cv * V, g[k]);
-                if (MODE2) loadv<T, V>(x2 + row * C + m.cv * V, a2[k]);
+                const int64_t ar = SMB_APPLY_ROW(m, row);
+                loadv<T, V>(x + ar * C + m.cv * V, a[k]);
+                loadv<T, V>(dy + ar * C + m.cv * V, g[k]);
+                if (MODE2) loadv<T, V>(x2 + ar * C + m.cv * V, a2[k]);
             }
         }
 #pragma unroll
@@ -393,8 +407,8 @@ __global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 :
                     o[v] = rs[v] * (gg - mg[v] - xh * mgx[v]);
                     o2[v] = MODE2 == 2 ? rs2[v] * (gg - mg[v] - xh2 * mgx2[v]) : gg;
                 }
-                storev<T, V>(dx + row * C + m.cv * V, o);
-                if (dx2) storev<T, V>(dx2 + row * C + m.cv * V, o2);
+                storev<T, V>(dx + SMB_APPLY_ROW(m, row) * C + m.cv * V, o);
+                if (dx2) storev<T, V>(dx2 + SMB_APPLY_ROW(m, row) * C + m.cv * V, o2);
             }
         }
     }
