@@ -51,6 +51,16 @@ __device__ __forceinline__ float act_grad(float v, int act, float slope) {
 #else
 #define SMB_APPLY_ROW(m, row) (row)
 #endif
+// The mirror image (variant in_rev_stats): the STATISTICS passes walk top-down, so they start with what the producer of the
+// tensor (a cuDNN convolution, if it writes in row order) left in L2, and end where the bottom-up apply pass starts.
+#ifndef SMB_IN_STATS_REVERSE
+#define SMB_IN_STATS_REVERSE 0
+#endif
+#if SMB_IN_STATS_REVERSE
+#define SMB_STATS_ROW(m, row) ((m).row_lo + (m).row_hi - 1 - (row))
+#else
+#define SMB_STATS_ROW(m, row) (row)
+#endif
 
 struct RowMap {
     int cv, r, RB;
@@ -98,8 +108,9 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_fwd_kernel(const NormP 
             float a[U][V], a2[U][V];
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                loadv<T, V>(x + (row + (int64_t)k * m.RB) * C + m.cv * V, a[k]);
-                if (kTwo) loadv<T, V>(x2 + (row + (int64_t)k * m.RB) * C + m.cv * V, a2[k]);
+                const int64_t sr = SMB_STATS_ROW(m, row + (int64_t)k * m.RB);
+                loadv<T, V>(x + sr * C + m.cv * V, a[k]);
+                if (kTwo) loadv<T, V>(x2 + sr * C + m.cv * V, a2[k]);
             }
 #pragma unroll
             for (int k = 0; k < U; ++k) {
@@ -112,11 +123,11 @@ __global__ void __launch_bounds__(kNormThreads) in_stats_fwd_kernel(const NormP 
         }
         for (; row < m.row_hi; row += m.RB) {
             float a[V];
-            loadv<T, V>(x + row * C + m.cv * V, a);
+            loadv<T, V>(x + SMB_STATS_ROW(m, row) * C + m.cv * V, a);
 #pragma unroll
             for (int v = 0; v < V; ++v) { const float d = a[v] - c1[v]; s1[v] += d; q1[v] = fmaf(d, d, q1[v]); }
             if (kTwo) {
-                loadv<T, V>(x2 + row * C + m.cv * V, a);
+                loadv<T, V>(x2 + SMB_STATS_ROW(m, row) * C + m.cv * V, a);
 #pragma unroll
                 for (int v = 0; v < V; ++v) { const float d = a[v] - c2[v]; s2[v] += d; q2[v] = fmaf(d, d, q2[v]); }
             }
@@ -286,9 +297,10 @@ __global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 :
             for (int k = 0; k < U; ++k) {
                 const int64_t row = row0 + (int64_t)k * m.RB;
                 if (row < m.row_hi) {
-                    loadv<T, V>(x + row * C + m.cv * V, a[k]);
-                    loadv<T, V>(dy + row * C + m.cv * V, g[k]);
-                    if (MODE2) loadv<T, V>(x2 + row * C + m.cv * V, a2[k]);
+                    const int64_t sr = SMB_STATS_ROW(m, row);
+                    loadv<T, V>(x + sr * C + m.cv * V, a[k]);
+                    loadv<T, V>(dy + sr * C + m.cv * V, g[k]);
+                    if (MODE2) loadv<T, V>(x2 + sr * C + m.cv * V, a2[k]);
                 }
             }
 #pragma unroll

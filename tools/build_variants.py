@@ -25,6 +25,7 @@ VARIANTS = {
     "in_minb4": (["-DSMB_IN_FWD_MINB=4", "-DSMB_IN_BWD_MINB0=4", "-DSMB_IN_BWD_MINB2=3"], ["instnorm.cu"], r"in_(apply|stats)"),
     # instance norm: the apply passes walk each CTA's row range top-down (what the preceding statistics pass left in L2 comes first)
     "in_rev": (["-DSMB_IN_APPLY_REVERSE=1"], ["instnorm.cu"], r"in_apply"),
+    "in_rev_stats": (["-DSMB_IN_STATS_REVERSE=1"], ["instnorm.cu"], r"in_stats"),
     # R3 with a register cap for 3 CTAs per SM (80 registers, ~0.5 KB of spills; its 55 KB of shared memory allow it)
     "r3_minb3": (["-DSMB_R3_MINB=3"], ["scan_bwd.cu"], r"scan_bwd_main_kernel"),
     # forward scan with 2 / 4 of the 8 state pairs on the packed-FMA polynomial ex2 (slower on the lockstep kernels, DESIGN.md 3.1;
