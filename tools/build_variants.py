@@ -28,10 +28,10 @@ VARIANTS = {
     "in_rev_stats": (["-DSMB_IN_STATS_REVERSE=1"], ["instnorm.cu"], r"in_stats"),
     # R3 with a register cap for 3 CTAs per SM (80 registers, ~0.5 KB of spills; its 55 KB of shared memory allow it)
     "r3_minb3": (["-DSMB_R3_MINB=3"], ["scan_bwd.cu"], r"scan_bwd_main_kernel"),
-    # forward scan with 2 / 4 of the 8 state pairs on the packed-FMA polynomial ex2 (slower on the lockstep kernels, DESIGN.md 3.1;
+    # forward scan and backward R1 with 2 / 4 of the 8 state pairs on the packed-FMA polynomial ex2 (slower on the lockstep kernels, DESIGN.md 3.1;
     # meant for the software-pipelined kernels, SMB_FWD_V2=1, whose MUFU utilisation should be higher)
-    "poly11": (["-DSMB_POLY_MASK=0x11"], ["scan_fwd.cu", "scan_fwd_v2.cu"], r"scan_fwd_(agg|main)"),
-    "poly33": (["-DSMB_POLY_MASK=0x33"], ["scan_fwd.cu", "scan_fwd_v2.cu"], r"scan_fwd_(agg|main)"),
+    "poly11": (["-DSMB_POLY_MASK=0x11"], ["scan_fwd.cu", "scan_fwd_v2.cu", "scan_bwd.cu", "scan_bwd_v2.cu"], r"scan_(fwd_(agg|main)|bwd_ragg)"),
+    "poly33": (["-DSMB_POLY_MASK=0x33"], ["scan_fwd.cu", "scan_fwd_v2.cu", "scan_bwd.cu", "scan_bwd_v2.cu"], r"scan_(fwd_(agg|main)|bwd_ragg)"),
     # conv1d with 256-thread CTAs
     "conv256": (["-DSMB_CONV_THREADS=256"], ["conv1d.cu"], r"conv1d_(fwd|bwd)_kernel"),
 }

@@ -79,7 +79,7 @@ if ! skip variants; then   # build-time tuning variants, if tools/build_variants
     v=$(basename $lib .so)
     SMB_LIB=$PWD/$lib timeout 300 python tools/microbench.py --dtypes bf16 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_$v.json > $O/${TAG}_mb_$v.log 2>&1
     SMB_LIB=$PWD/$lib timeout 300 python tools/op_breakdown.py > $O/${TAG}_breakdown_$v.log 2>&1
-    case $v in lib_poly*) SMB_LIB=$PWD/$lib SMB_FWD_V2=1 timeout 300 python tools/microbench.py --dtypes bf16 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_${v}_fwdv2.json > $O/${TAG}_mb_${v}_fwdv2.log 2>&1;; esac
+    case $v in lib_poly*) SMB_LIB=$PWD/$lib SMB_FWD_V2=1 SMB_RAGG_V2=1 timeout 300 python tools/microbench.py --dtypes bf16 --batches 2 --stages 0,1 --no-ref --out $O/${TAG}_mb_${v}_fwdv2.json > $O/${TAG}_mb_${v}_fwdv2.log 2>&1;; esac
   done
 fi
 if ! skip ncu; then  # launch list of one training step (kernel shares)
