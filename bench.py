@@ -44,7 +44,11 @@ def parse_args():
     ap.add_argument("--bf16-params", action="store_true",
                     help="bf16 matmul / convolution parameters with fp32 masters in the optimizer (segmamba_b200/master_weights.py): "
                          "same arithmetic as autocast, two multi-tensor copies per step instead of ~400 cast kernels")
-    ap.add_argument("--cpu-sample", type=int, default=32, help="edge of the cubic crop the CPU arm runs per step")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="edge of the cubic crop the CPU arm runs per step")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0: min(cores this process may use, 32))")
+    ap.add_argument("--no-ref-cuda", action="store_true",
+                    help="skip the vs_ref_cuda leg (reference op sequence on the reference's CUDA kernels from oracle/_ref)")
+    ap.add_argument("--ref-cuda-steps", type=int, default=5)
     return ap.parse_args()
 
 
@@ -96,14 +100,23 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (oracle/) on the host cores.  One step = forward + backward of one cubic crop.
 # ----------------------------------------------------------------------------------------------
-def cpu_step_factory(sample: int):
+def cpu_threads(requested: int = 0) -> int:
+    """threads of the CPU arm: the cores this process may run on (not os.cpu_count(): cgroup / affinity limits), capped at 32 --
+    the C oracle parallelises over channels and torch's CPU conv3d stops scaling long before 128 threads."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    return max(1, min(requested or 32, avail))
+
+
+def cpu_step_factory(sample: int, threads: int):
     import torch
     from oracle import oracle as orc
     from segmamba_b200.segmamba import SegMamba
     orc.build()
     orc.set_precision("f32")
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(threads)
     torch.manual_seed(0)
     model = SegMamba(in_chans=4, out_chans=4, depths=[2, 2, 2, 2], feat_size=[48, 96, 192, 384])   # weights only
     sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
@@ -120,32 +133,60 @@ def cpu_step_factory(sample: int):
 
     frac = (sample / PATCH) ** 3
     desc = (f"oracle port (C scan/conv1d with OpenMP + torch CPU convs), fp32, one {sample}^3 crop forward+backward per step = "
-            f"{frac:.4g} of a 128^3 patch; value = {frac:.4g} / seconds")
-    return step, frac, cores, desc
+            f"{frac:.4g} of a 128^3 patch; value = {frac:.4g} / seconds; {threads} threads (torch and OpenMP each, passive wait)")
+    return step, frac, threads, desc
 
 
-def run_cpu(steps: int, warmup: int, sample: int):
-    step, frac, cores, desc = cpu_step_factory(sample)
+def run_cpu(steps: int, warmup: int, sample: int, threads: int):
+    """in-process CPU arm; call through run_cpu_child() so that the thread environment is the same wherever bench.py runs."""
+    step, frac, cores, desc = cpu_step_factory(sample, threads)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"value": frac / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds_per_step": dt}
+    return {"value": frac / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds_per_step": dt,
+            "same_config": sample == PATCH}
+
+
+def run_cpu_child(steps: int, warmup: int, sample: int, threads: int, timeout_s: float = 900.0):
+    """The CPU arm in a child process with an explicit thread environment.  Round 1 ran it in-process: 128 torch threads on
+    top of a second OpenMP runtime's 128 spinning threads took 47 s/step, the same code under torchrun's OMP_NUM_THREADS=1
+    took 1.9 s/step.  The child gets OMP_NUM_THREADS = MKL_NUM_THREADS = n, OMP_WAIT_POLICY=passive (idle pools sleep instead
+    of spinning against each other) and none of the launcher's rank variables."""
+    import subprocess
+    n = cpu_threads(threads)
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_PROC_BIND", "GOMP_CPU_AFFINITY",
+                        "KMP_AFFINITY", "TORCHELASTIC_RUN_ID", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE")}
+    env.update(OMP_NUM_THREADS=str(n), MKL_NUM_THREADS=str(n), OMP_WAIT_POLICY="passive", GOMP_SPINCOUNT="0",
+               SMB_CPU_CHILD="1", CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup),
+           "--cpu-sample", str(sample), "--cpu-threads", str(n)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout_s)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError(f"CPU arm child failed (rc {r.returncode}): {r.stderr[-2000:]}")
+    return json.loads(lines[-1])
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = run_cpu(args.steps, args.warmup, args.cpu_sample)
+    if os.environ.get("SMB_CPU_CHILD") != "1":
+        print(json.dumps(run_cpu_child(args.steps, args.warmup, args.cpu_sample, args.cpu_threads)))
+        return
+    res = run_cpu(args.steps, args.warmup, args.cpu_sample, cpu_threads(args.cpu_threads))
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": res["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "global_batch": 1, "note": "CPU arm: the reference has no CPU path for the "
-                   "model (Mamba.forward v3 is CUDA-only); this is the oracle port of it on the host cores"},
+        "config": {"workload": workload_name(args), "global_batch": 1, "same_config": res["same_config"],
+                   "note": "CPU arm: the reference has no CPU path for the model (Mamba.forward v3 is CUDA-only); this is the "
+                           "oracle port of it on the host cores, one crop per step scaled by volume.  The like-for-like "
+                           "baseline (reference CUDA kernels, same patch / batch / dtype) is the native arm's vs_ref_cuda key."},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -216,6 +257,46 @@ def _start_stall_watchdog(rank, limit_s=420.0):
                 os._exit(3)
 
     threading.Thread(target=watch, daemon=True, name="bench-stall-watchdog").start()
+
+
+def run_ref_cuda_leg(args, native_ms_per_step, log):
+    """The denominator of north_star's ">= 5x the reference CUDA path": the reference's op sequence (NCDHW, flips / stack /
+    rearrange copies, ATen InstanceNorm3d / LayerNorm, cuDNN / cuBLAS as the reference calls them) on the reference's OWN CUDA
+    kernels compiled for sm_100a (oracle/_ref/*.so, oracle/build_ref.py), same patch / batch / bf16 autocast / optimizer, timed
+    on the same GPU right after the native arm's timed region.  Baseline only: nothing here is on the product path."""
+    import gc
+    import importlib.util
+    import torch
+    try:
+        spec = importlib.util.spec_from_file_location("ref_equivalent_step", os.path.join(ROOT, "tools", "ref_equivalent_step.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "selective_scan_cuda.so")):
+            return {"unavailable": "oracle/_ref/*.so not built (python oracle/build_ref.py in the build container)"}
+        gc.collect()
+        torch.cuda.empty_cache()
+        log(0, "vs_ref_cuda leg: reference op sequence on the reference CUDA kernels")
+        ref_step, params = mod.make_ref_step(args.batch, args.patch, "cuda")
+        for _ in range(2):
+            ref_step()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.ref_cuda_steps):
+            loss = ref_step()
+        e.record()
+        torch.cuda.synchronize()
+        ref_ms = s.elapsed_time(e) / args.ref_cuda_steps
+        out = {"ref_ms_per_step": ref_ms, "ref_patches_per_s": args.batch / (ref_ms / 1e3), "native_ms_per_step": native_ms_per_step,
+               "ratio": ref_ms / native_ms_per_step, "steps": args.ref_cuda_steps, "ref_loss": float(loss.detach()),
+               "kind": "reference CUDA ext (selective_scan_cuda + causal_conv1d_cuda, sm_100a build) + reference op sequence, "
+                       "bf16 autocast, batch %d, %d^3 patch, same GPU" % (args.batch, args.patch)}
+        del ref_step, params
+        gc.collect()
+        torch.cuda.empty_cache()
+        return out
+    except Exception as ex:
+        return {"error": repr(ex)[-400:]}
 
 
 def main_native(args):
@@ -341,9 +422,18 @@ def main_native(args):
 
     W = max(args.warmup, 3)
     _log(rank, f"model built; {W} warm-up steps")
+    layout_seen = {}
+
+    def _layout_hook(mod, inp, out):
+        layout_seen[type(mod).__name__] = bool(out.dim() == 5 and out.is_contiguous(memory_format=torch.channels_last_3d)
+                                                and not out.is_contiguous())
+    hooks = [model.encoder1.register_forward_hook(_layout_hook), model.vit.gscs[0].register_forward_hook(_layout_hook),
+             model.decoder2.register_forward_hook(_layout_hook)] if graphed is None else []
     for _ in range(W):
         step(x_dev, y_dev)
     barrier()
+    for h in hooks:
+        h.remove()
     _log(rank, "warm-up done; timing")
     # host-side enqueue time of one step (no synchronisation inside): tells how close the step is to launch-bound
     t0 = time.perf_counter()
@@ -405,25 +495,33 @@ def main_native(args):
                 "kernel": f"smb_{op} (all passes) at batch={meta[0]} dim={meta[1]} L={meta[2]} N={meta[3]} elt={meta[4]}B",
                 "algorithmic_bytes": by, "avg_ms": ms, "launches_timed": len(d), "peak_source": peak_src}
 
-    roofline = roof("scan_fwd", scan_fwd_bytes)
+    roof_fwd = roof("scan_fwd", scan_fwd_bytes)
     roof_bwd = roof("scan_bwd", scan_bwd_bytes)
     # The forward scan is co-bound by the MUFU pipe: one ex2 per (b, d, t, n) update in each of its two passes.
     # Extra key, not part of the contract: ex2 throughput against 148 SMs x 16 lanes/clk at the SM clock sampled under load.
     roof_mufu = None
     try:
-        if roofline and clocks and clocks.get("sm_mhz"):
-            b_, d_, l_, n_ = [int(v) for v in re.findall(r"batch=(\d+) dim=(\d+) L=(\d+) N=(\d+)", roofline["kernel"])[0]]
+        if roof_fwd and clocks and clocks.get("sm_mhz"):
+            b_, d_, l_, n_ = [int(v) for v in re.findall(r"batch=(\d+) dim=(\d+) L=(\d+) N=(\d+)", roof_fwd["kernel"])[0]]
             ex2 = 2.0 * b_ * d_ * l_ * n_
-            ach = ex2 / (roofline["avg_ms"] * 1e-3) / 1e12
+            ach = ex2 / (roof_fwd["avg_ms"] * 1e-3) / 1e12
             peak = 148 * 16 * float(clocks["sm_mhz"]) * 1e6 / 1e12
             roof_mufu = {"bound": "mufu", "achieved": ach, "peak": peak, "unit": "Tex2/s", "frac": ach / peak,
-                         "ex2_per_call": ex2, "kernel": roofline["kernel"]}
+                         "ex2_per_call": ex2, "kernel": roof_fwd["kernel"]}
     except Exception:
         roof_mufu = None
     native_ms = {}
     prof_steps = args.steps if graphed is None else 2
     for (op, meta), d in durs.items():
         native_ms[op] = native_ms.get(op, 0.0) + sum(d) / prof_steps
+    # `roofline` = the native op with the largest share of the step among those with a byte model (the scans); the other one
+    # stays as an extra key
+    cands = [(native_ms.get("scan_bwd", 0.0), roof_bwd), (native_ms.get("scan_fwd", 0.0), roof_fwd)]
+    roofline = max([c for c in cands if c[1] is not None], key=lambda c: c[0], default=(0.0, None))[1]
+
+    vs_ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_ref_cuda and graphed is None:
+        vs_ref_cuda = run_ref_cuda_leg(args, ms_per_step, _log)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
@@ -431,17 +529,22 @@ def main_native(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2: one step touches > 10 GB of activations (126 MB L2)",
-                       "channels_last_3d": True, "cuda_graph": bool(args.cuda_graph), "bf16_params": bool(args.bf16_params)},
+                       "channels_last_3d": (all(layout_seen.values()) if layout_seen else None), "cuda_graph": bool(args.cuda_graph), "bf16_params": bool(args.bf16_params)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_scan_fwd": roof_fwd,
             "roofline_scan_bwd": roof_bwd,
+            "vs_ref_cuda": vs_ref_cuda,
             "roofline_mufu": roof_mufu,
             "native_ms_per_step": native_ms,
             "host_enqueue_ms_per_step": host_ms,
         }
         if world == 1 and not args.no_cpu_baseline:
-            res = run_cpu(1, 0, args.cpu_sample)
-            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:
+                res = run_cpu_child(1, 1, args.cpu_sample, args.cpu_threads)
+                line["cpu_baseline"] = res["cpu_baseline"]
+            except Exception as ex:                        # the GPU numbers must not be lost to a CPU-leg problem
+                line["cpu_baseline"] = {"error": str(ex)[-300:]}
         print(json.dumps(line))
     if world > 1:
         _log(rank, "done")

@@ -123,14 +123,10 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
         acc = None
 
     for i0 in range(0, len(mine), sw_batch_size):
-        chunk = mine[i0:i0 + sw_batch_size]
-        # a batch never mixes flips (keeps one accumulator live)
-        chunk = [c for c in chunk if c[0] == chunk[0][0]]
-        rest = mine[i0 + len(chunk):i0 + sw_batch_size]
-        for part in (chunk, rest):
-            if not part:
-                continue
-            fi = part[0][0]
+        # a predictor batch never mixes flips (one accumulator is live at a time): a batch that spans several flips --
+        # few windows per flip, e.g. image <= roi with sw_batch_size >= 3, or a thin shard -- is split into one run per flip
+        for fi, run in itertools.groupby(mine[i0:i0 + sw_batch_size], key=lambda c: c[0]):
+            part = list(run)
             if xin_flip != fi:
                 flush()
                 fl = flips[fi]

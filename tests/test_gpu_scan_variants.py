@@ -1,0 +1,65 @@
+"""Every alternative scan kernel that a build/run switch can select (SMB_FWD_V2 = 1: cp.async-pipelined forward, 2: TMA-staged
+forward; SMB_RAGG_V2: pipelined reverse aggregate; SMB_R3_V2: second-generation main backward pass) against the CPU ORACLE --
+not against the default kernels -- at a ragged small size (partial tiles, partial channel octets, scalar tails) and at the
+BASELINE stage-0 size (batch 1, D=96, L=262144, N=16: every segment / carry / vector-reduction path at full length).
+A switch whose kernel fails here is removed from the tree, not masked."""
+import pytest
+import torch
+
+from test_gpu_scan import _compare_grads, _oracle_fwd_bwd
+from util import GRAD_TOL, TOL, assert_close, rand_scan_inputs
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {
+    "default": {},
+    "fwd_cp_async": {"SMB_FWD_V2": "1"},
+    "fwd_tma": {"SMB_FWD_V2": "2"},
+    "ragg_v2": {"SMB_RAGG_V2": "1"},
+    "r3_v2": {"SMB_R3_V2": "1"},
+    "all": {"SMB_FWD_V2": "2", "SMB_RAGG_V2": "1", "SMB_R3_V2": "1"},
+}
+ALL_SWITCHES = ("SMB_FWD_V2", "SMB_RAGG_V2", "SMB_R3_V2")
+_oracle_cache = {}
+
+
+def _oracle_cached(key, d, flip):
+    if key not in _oracle_cache:
+        _oracle_cache.clear()                     # one full-size oracle result (a few hundred MB) alive at a time
+        _oracle_cache[key] = _oracle_fwd_bwd(d, flip=flip)
+    return _oracle_cache[key]
+
+
+def _run(d, direction, monkeypatch, env):
+    from segmamba_b200 import selective_scan_cuda as ssc
+    for k in ALL_SWITCHES:
+        monkeypatch.setenv(k, env.get(k, "0"))
+    B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
+    out, x, out_z, hst = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, direction=direction,
+                                    want_out=True, want_x=True, want_hstates=True)
+    g = ssc.bwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], d["dout"], None, True, True,
+                   direction=direction, hstates=hst, low_memory=True)
+    torch.cuda.synchronize()
+    return out, x, out_z, g
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS), ids=list(VARIANTS))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=["bf16", "f16", "f32"])
+@pytest.mark.parametrize("direction", [0, 1], ids=["fwd", "rev"])
+@pytest.mark.parametrize("shape", [(2, 44, 5003), (1, 96, 262144)], ids=["ragged", "stage0"])
+def test_scan_variant_vs_oracle(monkeypatch, variant, dtype, direction, shape):
+    env = VARIANTS[variant]
+    if dtype == torch.float32 and variant in ("fwd_cp_async", "fwd_tma", "ragg_v2"):
+        pytest.skip("16-bit activation kernels")
+    if shape[2] > 100000 and dtype == torch.float16:
+        pytest.skip("full size: bf16 and fp32 only")
+    batch, dim, L = shape
+    d = rand_scan_inputs(31 + L, batch, dim, L, 16, 1, dtype)
+    out, x, out_z, g = _run(d, direction, monkeypatch, env)
+    y, oz, last, xc, go = _oracle_cached((shape, dtype, direction), d, bool(direction))
+    tol = TOL[dtype]
+    assert_close(out, y, tol, "out")
+    assert_close(out_z, oz, tol, "out_z")
+    assert_close(g[8], oz, tol, "recomputed out_z")
+    assert_close(x[..., 1::2], xc[..., 1::2], tol, "x (chunk states)")
+    _compare_grads(g, go, dtype, True, variant + ":")

@@ -1,0 +1,65 @@
+"""Training-step options on the GPU: side streams for the three scan directions, bf16 parameters with fp32 masters (f3)."""
+import pytest
+import torch
+
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def test_direction_streams_match_serial(monkeypatch):
+    """SMB_DIR_STREAMS=1: the reversed and inter-slice passes of every mixer run on side streams; outputs and gradients must
+    equal the single-stream execution (same kernels, same order inside each branch), eagerly and after repeated steps
+    (allocator reuse across streams)."""
+    import golden_inputs as gi
+    from segmamba_b200 import mamba_simple
+    from segmamba_b200.segmamba import SegMamba
+    c = gi.MODEL_CASE
+    torch.manual_seed(5)
+    m = SegMamba(in_chans=4, out_chans=4, depths=c["depths"], feat_size=c["feat_size"], hidden_size=c["hidden_size"]).cuda().train()
+    x = torch.rand(2, 4, 32, 32, 32, device="cuda")
+    res = []
+    for on in (False, True, True):
+        monkeypatch.setattr(mamba_simple, "DIRECTION_STREAMS", on)
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = m(x).float()
+        y.square().mean().backward()
+        torch.cuda.synchronize()
+        res.append((y.detach().clone(), [p.grad.detach().clone() for p in m.parameters()]))
+    scale = max(float(g0.abs().max()) for g0 in res[0][1])
+    for k in (1, 2):
+        assert_close(res[k][0], res[0][0], 1e-5, "logits, streams vs serial")
+        for g1, g0 in zip(res[k][1], res[0][1]):
+            if float(g0.abs().max()) > 1e-3 * scale:    # conv biases in front of an instance norm: pure round-off gradients
+                assert_close(g1, g0, 2e-2, "parameter gradient, streams vs serial")     # fp32 atomics: order-dependent rounding
+
+
+def test_master_weights_step_matches_autocast_step():
+    """bf16 parameters + fp32 masters (segmamba_b200/master_weights.py) on the real model: the same losses and fp32 weights as
+    the plain autocast step over three iterations, up to the run-to-run noise of the fp32 atomics (CPU twin of this test is
+    bit-exact, tests/test_train_step.py)."""
+    import copy
+    import golden_inputs as gi
+    from segmamba_b200.master_weights import MasterWeights
+    from segmamba_b200.segmamba import SegMamba
+    from segmamba_b200.train_step import TrainStep
+    c = gi.MODEL_CASE
+    torch.manual_seed(7)
+    ref_model = SegMamba(in_chans=4, out_chans=4, depths=c["depths"], feat_size=c["feat_size"], hidden_size=c["hidden_size"]).cuda()
+    model = copy.deepcopy(ref_model)
+    mk = lambda params: torch.optim.SGD(params, lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    ref = TrainStep(ref_model, mk(ref_model.parameters()), torch.nn.CrossEntropyLoss())
+    mw = MasterWeights(model)
+    assert len(mw.converted_names()) > 100 and model.vit.stages[0][0].mamba.A_log.dtype == torch.float32
+    step = TrainStep(model, mk(mw.optimizer_parameters()), torch.nn.CrossEntropyLoss(), master_weights=mw)
+    g = torch.Generator().manual_seed(1)
+    for i in range(3):
+        x = torch.rand(2, 4, 32, 32, 32, generator=g).cuda()
+        y = torch.randint(0, 4, (2, 32, 32, 32), generator=g).cuda()
+        la, lb = float(ref(x, y)), float(step(x, y))
+        assert abs(la - lb) <= 2e-3 * abs(la), (i, la, lb)
+    sd = mw.state_dict()
+    for k, v in ref_model.state_dict().items():
+        assert sd[k].dtype == v.dtype
+        assert_close(sd[k], v, 2e-2, k)

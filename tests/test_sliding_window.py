@@ -54,6 +54,49 @@ def test_mirror_tta_is_whole_volume_flip():
     assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
 
 
+def test_mirror_tta_batches_spanning_several_flips():
+    """sw_batch_size larger than the work items of one flip (image <= roi: one window per flip): a predictor batch would
+    span several flips; every run of equal flip must go to its own accumulator.  8 flips x 1 window, batch sizes 1..5."""
+    x = gi.model_input(54, (1, 2, 8, 8, 8))
+    pred = _predictor()
+    ref = sw.sliding_window_inference(x, (8, 8, 8), 1, pred, mirror_axes=(0, 1, 2))
+    manual = sum(torch.flip(pred(torch.flip(x, d) if d else x), d) if d else pred(x)
+                 for d in [(), (2,), (3,), (4,), (2, 3), (2, 4), (3, 4), (2, 3, 4)]) / 8
+    assert torch.allclose(ref, manual, rtol=1e-5, atol=1e-6)
+    for bs in (2, 3, 4, 5):
+        got = sw.sliding_window_inference(x, (8, 8, 8), bs, pred, mirror_axes=(0, 1, 2))
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6), f"sw_batch_size={bs}"
+    # two windows per flip, batch of 3: runs of (2, 1), (1, 2), ...
+    x2 = gi.model_input(55, (1, 2, 12, 8, 8))
+    ref2 = sw.sliding_window_inference(x2, (8, 8, 8), 1, pred, mirror_axes=(0, 1, 2))
+    for bs in (3, 5):
+        assert torch.allclose(sw.sliding_window_inference(x2, (8, 8, 8), bs, pred, mirror_axes=(0, 1, 2)), ref2,
+                              rtol=1e-5, atol=1e-6)
+
+
+def _worker_thin(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = gi.model_input(54, (1, 2, 8, 8, 8))
+        out = sw.sliding_window_inference(x, (8, 8, 8), 4, _predictor(), group=True, assemble_on=None, mirror_axes=(0, 1, 2))
+        ret[f"thin{rank}"] = out.numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_thin_shards_spanning_flips_two_ranks_gloo():
+    """world 2, one window per flip, sw_batch_size 4: every rank's batches span four flips."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_thin, args=(2, port, ret), nprocs=2, join=True)
+    x = gi.model_input(54, (1, 2, 8, 8, 8))
+    single = sw.sliding_window_inference(x, (8, 8, 8), 1, _predictor(), mirror_axes=(0, 1, 2))
+    assert np.allclose(ret["thin0"], single.numpy(), rtol=1e-5, atol=1e-6)
+    assert np.allclose(ret["thin1"], single.numpy(), rtol=1e-5, atol=1e-6)
+
+
 def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

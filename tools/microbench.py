@@ -102,6 +102,11 @@ def main():
                                           args.iters, flush)
                 r["conv_fwd_ms"] = timeit(lambda: cc.causal_conv1d_fwd(u, w, cb, True), args.iters, flush)
                 r["conv_bwd_ms"] = timeit(lambda: cc.causal_conv1d_bwd(u, w, cb, dout, None, True), args.iters, flush)
+                ns = {262144: 64, 32768: 32, 4096: 16, 512: 8}.get(L, 8)
+                xz = torch.randn(2 * D, batch, L, device=dev).to(dt).permute(1, 0, 2)      # channel-major xz, as in the mixer
+                r["permute_ms"] = timeit(lambda: cc.seq_permute(xz, ns), args.iters, flush)
+                r["permute_gbs"] = 2 * s * batch * 2 * D * L / r["permute_ms"] / 1e6
+                del xz
                 r["scan_fwd_gbs"] = fwd_bytes / r["scan_fwd_ms"] / 1e6
                 r["scan_bwd_gbs"] = bwd_bytes / r["scan_bwd_ms"] / 1e6
                 r["conv_fwd_gbs"] = conv_bytes / r["conv_fwd_ms"] / 1e6

@@ -81,6 +81,36 @@ def bind_reference_kernels(orc):
     orc.causal_conv1d = lambda x, weight, bias=None, activation=None: RefConv.apply(x, weight, bias, activation in ("silu", "swish"))
 
 
+def make_ref_step(batch=2, patch=128, dev="cuda"):
+    """(step_fn, params): one training step of the reference op sequence on the reference CUDA kernels (oracle/_ref), same
+    optimizer / clip / bf16 autocast as bench.py's native arm.  Used by bench.py's ``vs_ref_cuda`` leg and by main() below."""
+    from oracle import oracle as orc
+    from segmamba_b200.segmamba import SegMamba
+    bind_reference_kernels(orc)
+    torch.backends.cudnn.benchmark = True
+    depths, feat, hidden = [2, 2, 2, 2], [48, 96, 192, 384], 768
+    torch.manual_seed(0)
+    model = SegMamba(in_chans=4, out_chans=4, depths=depths, feat_size=feat, hidden_size=hidden)   # parameters only: same init
+    params = {k: torch.nn.Parameter(v.detach().clone().to(dev).contiguous()) for k, v in model.state_dict().items()}
+    del model
+    opt = torch.optim.SGD(list(params.values()), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    nsl = tuple(patch // 2 // (2 ** i) for i in range(4))
+    g = torch.Generator().manual_seed(42)
+    x = torch.rand(batch, 4, patch, patch, patch, generator=g).to(dev)
+    y = torch.randint(0, 4, (batch, patch, patch, patch), generator=g).to(dev)
+
+    def ref_step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = orc.segmamba_forward(params, x, depths=tuple(depths), nslices=nsl)
+            loss = torch.nn.functional.cross_entropy(logits.float(), y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 12.0)
+        opt.step()
+        return loss
+    return ref_step, params
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
