@@ -46,6 +46,10 @@ def parse_args():
                          "same arithmetic as autocast, two multi-tensor copies per step instead of ~400 cast kernels")
     ap.add_argument("--cpu-sample", type=int, default=64, help="edge of the cubic crop the CPU arm runs per step")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0: min(cores this process may use, 32))")
+    ap.add_argument("--workload", default="train_step", choices=["train_step", "sliding_window"],
+                    help="train_step: BASELINE.json configs[2] (the headline metric).  sliding_window: configs[4] -- one 240x240x155 "
+                         "4-modality volume, roi 128^3, overlap 0.5, gaussian blend, x8 mirror TTA, windows sharded over the ranks")
+    ap.add_argument("--no-tta", action="store_true", help="sliding_window: skip the 8 mirrored passes")
     ap.add_argument("--no-ref-cuda", action="store_true",
                     help="skip the vs_ref_cuda leg (reference op sequence on the reference's CUDA kernels from oracle/_ref)")
     ap.add_argument("--ref-cuda-steps", type=int, default=5)
@@ -551,9 +555,116 @@ def main_native(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------
+# sliding-window inference (BASELINE.json configs[4]; 4_predict.py:55-59 + prediction.py:110-159)
+# ----------------------------------------------------------------------------------------------
+def main_sliding_window(args):
+    """One step = one whole 4x155x240x240 volume: 18 windows of 128^3 (stride 64) x 8 mirrored passes = 144 patch forwards,
+    gaussian-blended on the device.  Windows are sharded `work[rank::world]` with no data-path collective; the only exchange
+    is the final reduce of the weighted accumulator to rank 0.  value = volumes/s over all ranks (strong scaling: the work per
+    volume is fixed), `patches_per_s` = window forwards per second.  With N > 1 rank 0 also runs the whole volume alone after
+    the timed region and reports the deviation of the sharded result from it."""
+    import torch
+    import torch.distributed as dist
+    from segmamba_b200 import _lib
+    from segmamba_b200.segmamba import SegMamba
+    from segmamba_b200.sliding_window import sliding_window_inference, window_starts
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import datetime
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        os.environ.setdefault("NCCL_MNNVL_ENABLE", "0")
+        _start_stall_watchdog(rank, 600.0)
+        dist.init_process_group(backend="nccl", device_id=dev, timeout=datetime.timedelta(minutes=10))
+        dist.barrier()
+    _lib.lib()
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    model = SegMamba(in_chans=4, out_chans=4, depths=[2, 2, 2, 2], feat_size=[48, 96, 192, 384]).to(dev).eval()
+    if world > 1:                                     # same weights everywhere (each rank seeded identically anyway)
+        for p_ in model.parameters():
+            dist.broadcast(p_.data, 0)
+    g = torch.Generator().manual_seed(7)
+    vol_host = torch.rand(1, 4, 155, 240, 240, generator=g).pin_memory()            # 4_predict.py: BraTS volume, 4 modalities
+    roi = (args.patch,) * 3
+    axes = None if args.no_tta else (0, 1, 2)
+    n_win = len(window_starts((155, 240, 240), roi, 0.5)) * (1 if args.no_tta else 8)
+    out_host = torch.empty(1, 4, 155, 240, 240).pin_memory() if rank == 0 else None
+
+    def predict(x, group):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return sliding_window_inference(x, roi, args.batch, lambda t: model(t).float(), overlap=0.5, mode="gaussian",
+                                            mirror_axes=axes, group=group, assemble_on=0)
+
+    def step():
+        x = vol_host.to(dev, non_blocking=True)                                     # H2D inside the timed region
+        out = predict(x, True if world > 1 else None)
+        if rank == 0:
+            out_host.copy_(out, non_blocking=True)                                  # D2H of the blended logits
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(args.warmup, 1)
+    _log(rank, f"sliding window: {n_win} window forwards per volume, {W} warm-up volumes")
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    l0 = _lib.launch_count()
+    sampler.start()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        out = step()
+    e.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([s.elapsed_time(e)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_vol = float(ms.item()) / args.steps
+    launches = _lib.launch_count() - l0
+    dev_vs_single = None
+    if world > 1 and rank == 0:
+        ref = predict(vol_host.to(dev), None)
+        dev_vs_single = float((out - ref).abs().max() / ref.abs().max())
+    if rank == 0:
+        line = {
+            "metric": "volumes_per_sec_sliding_window_240x240x155_4ch", "value": 1e3 / ms_per_vol, "unit": "volumes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms_per_vol, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"SegMamba default, sliding-window inference of one 4x155x240x240 volume, roi {args.patch}^3, overlap 0.5, "
+                                   f"gaussian, sw_batch_size {args.batch}, {'no TTA' if args.no_tta else 'x8 mirror TTA'} "
+                                   "(BASELINE.json configs[4])",
+                       "window_forwards_per_volume": n_win, "parallelism": f"windows[rank::{world}]",
+                       "l2": "inputs larger than L2 (one window forward touches > 3 GB)"},
+            "patches_per_s": n_win * 1e3 / ms_per_vol, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": 1e3 / ms_per_vol, "unit": "volumes/s", "h2d_bytes_per_step": int(vol_host.numel() * 4),
+                    "d2h_bytes_per_step": int(out_host.numel() * 4),
+                    "note": "the timed region already includes the H2D copy of the volume and the D2H copy of the blended logits"},
+            "sharded_vs_single_rank_max_rel": dev_vs_single,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         main_reference(a)
+    elif a.workload == "sliding_window":
+        main_sliding_window(a)
     else:
         main_native(a)

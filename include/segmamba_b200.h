@@ -17,6 +17,9 @@
  *   smb_layernorm_*   nn.LayerNorm(dim) of MambaLayer, model_segmamba/segmamba.py:54,70
  *   smb_seq_permute   the flip / inter-slice re-orderings of Mamba.forward (v3),
  *                     mamba/mamba_ssm/modules/mamba_simple.py:230-261
+ *   smb_gemm          the pointwise contractions (library GEMMs / 1x1x1 cuDNN convolutions in the reference):
+ *                     Mamba.in_proj / out_proj  mamba_simple.py:204-208,264;  MlpChannel.fc1 / fc2  segmamba.py:81-89;
+ *                     GSC.proj3 / proj4  segmamba.py:103-107;  UnetResBlock.conv3  dynunet_block.py:66-69
  *
  * Scope: real A, input-dependent ("variable") B and C, dstate in {8, 16},
  * conv width 2..4, non-channel-last conv layout, fp32 / fp16 / bf16 I/O with fp32 arithmetic.
@@ -257,6 +260,39 @@ typedef struct smb_layernorm_bwd_args {
 
 SMB_API int smb_layernorm_fwd(const smb_layernorm_args *args, void *cuda_stream);
 SMB_API int smb_layernorm_bwd(const smb_layernorm_bwd_args *args, void *cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM (tcgen05.mma, accumulator in tensor memory, operands staged by TMA):
+ *     D[M, N] = epilogue( A[M, K] . B[N, K]^T )        fp16 / bf16 operands, fp32 accumulation
+ * a_major / b_major: SMB_MAJOR_K  -- the operand is stored (rows = M or N index, K contiguous), ld = row stride;
+ *                    SMB_MAJOR_MN -- the operand is stored (rows = K index, M or N contiguous), ld = row stride.
+ * so a (tokens, C) channels-last activation is K-major for a contraction over C and MN-major for a contraction
+ * over the tokens (weight gradients), and a (C_out, C_in) weight is K-major for y = x W^T and MN-major for dx = dy W.
+ * lda / ldb in elements, multiples of 8; A and B 16-byte aligned.  D: (M, N) row-major with row stride ldd, in
+ * out_dtype (SMB_F32 or the operand dtype).  epilogue: SMB_EPI_NONE, SMB_EPI_BIAS_N (+ bias[n], fp32),
+ * SMB_EPI_BIAS_N_GELU (exact erf GELU after the bias, nn.GELU()), SMB_EPI_BIAS_M (+ bias[m]).
+ * split_k > 1 (fp32 output only) partitions K over CTAs and ACCUMULATES into D with fp32 atomics; the caller
+ * zero-initialises D (as with the reference's zero-initialised gradient accumulators).  accumulate != 0 does the
+ * same with split_k == 1.
+ * ---------------------------------------------------------------------------------------------- */
+enum { SMB_MAJOR_K = 0, SMB_MAJOR_MN = 1 };
+enum { SMB_EPI_NONE = 0, SMB_EPI_BIAS_N = 1, SMB_EPI_BIAS_N_GELU = 2, SMB_EPI_BIAS_M = 3 };
+
+typedef struct smb_gemm_args {
+    int32_t M, N, K;
+    int32_t dtype;              /* SMB_F16 / SMB_BF16 (operands) */
+    int32_t out_dtype;          /* SMB_F32 or == dtype */
+    int32_t a_major, b_major;   /* SMB_MAJOR_* */
+    int32_t epilogue;           /* SMB_EPI_* */
+    int32_t split_k;            /* >= 1 */
+    int32_t accumulate;         /* fp32 output: atomically add into D */
+    const void *A, *B;
+    const float *bias;          /* may be NULL */
+    void *D;
+    int64_t lda, ldb, ldd;
+} smb_gemm_args;
+
+SMB_API int smb_gemm(const smb_gemm_args *args, void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,11 @@ class LayerNormBwdArgs(ctypes.Structure):
                 + [(n, _vp) for n in ("x", "dy", "gamma", "dx", "dgamma", "dbeta")])
 
 
+class GemmArgs(ctypes.Structure):
+    _fields_ = ([(n, _i32) for n in ("M", "N", "K", "dtype", "out_dtype", "a_major", "b_major", "epilogue", "split_k", "accumulate")]
+                + [(n, _vp) for n in ("A", "B", "bias", "D")] + [(n, _i64) for n in ("lda", "ldb", "ldd")])
+
+
 # every symbol include/segmamba_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = {
     "smb_version": (ctypes.c_int, []),
@@ -114,6 +119,7 @@ EXPORTS = {
     "smb_instnorm_bwd": (ctypes.c_int, [ctypes.POINTER(InstNormBwdArgs), _vp]),
     "smb_layernorm_fwd": (ctypes.c_int, [ctypes.POINTER(LayerNormArgs), _vp]),
     "smb_layernorm_bwd": (ctypes.c_int, [ctypes.POINTER(LayerNormBwdArgs), _vp]),
+    "smb_gemm": (ctypes.c_int, [ctypes.POINTER(GemmArgs), _vp]),
 }
 
 _lib = None

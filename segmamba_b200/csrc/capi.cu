@@ -7,12 +7,18 @@
 
 #include "../../include/segmamba_b200.h"
 #include "conv_internal.h"
+#include "gemm_internal.h"
 #include "norm_internal.h"
 #include "scan_internal.h"
 
 namespace smb {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+#ifdef SMB_EMU
+// tcgen05 / tensor memory have no CPU emulation: the emulated library exports smb_gemm but every call fails loudly
+cudaError_t gemm_tc_launch(GemmP, const void *, int64_t, const void *, int64_t, cudaStream_t) { return cudaErrorNotSupported; }
+int gemm_pick_bn(int) { return 0; }
+#endif
 }  // namespace smb
 
 namespace {
@@ -355,6 +361,35 @@ SMB_API int smb_layernorm_bwd(const smb_layernorm_bwd_args *a, void *cuda_stream
     p.dgamma = a->dgamma; p.dbeta = a->dbeta;
     cudaError_t e = smb::layernorm_dispatch(p, a->dtype, true, (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return cuda_fail(e, "smb_layernorm_bwd");
+    return SMB_OK;
+}
+
+SMB_API int smb_gemm(const smb_gemm_args *a, void *cuda_stream) {
+    if (!a) return fail(SMB_EINVAL, "smb_gemm: null args");
+    if (!a->A || !a->B || !a->D) return fail(SMB_EINVAL, "smb_gemm: A, B, D are required");
+    if (a->M <= 0 || a->N <= 0 || a->K <= 0) return fail(SMB_EINVAL, "smb_gemm: M, N, K must be positive");
+    if (a->dtype != SMB_F16 && a->dtype != SMB_BF16) return fail(SMB_EUNSUPPORTED, "smb_gemm: operands must be fp16 or bf16");
+    if (a->out_dtype != SMB_F32 && a->out_dtype != a->dtype) return fail(SMB_EINVAL, "smb_gemm: out_dtype must be fp32 or the operand dtype");
+    if ((a->lda % 8) || (a->ldb % 8)) return fail(SMB_EINVAL, "smb_gemm: lda and ldb must be multiples of 8 elements (16-byte rows for TMA)");
+    if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15))
+        return fail(SMB_EINVAL, "smb_gemm: A and B must be 16-byte aligned");
+    if (a->a_major < 0 || a->a_major > 1 || a->b_major < 0 || a->b_major > 1) return fail(SMB_EINVAL, "smb_gemm: bad operand major");
+    if (a->epilogue < SMB_EPI_NONE || a->epilogue > SMB_EPI_BIAS_M) return fail(SMB_EINVAL, "smb_gemm: bad epilogue");
+    if ((a->split_k > 1 || a->accumulate) && a->out_dtype != SMB_F32)
+        return fail(SMB_EINVAL, "smb_gemm: split_k / accumulate need an fp32 output");
+    if (a->ldd < a->N) return fail(SMB_EINVAL, "smb_gemm: ldd < N");
+    // the contiguous extent of each operand as stored: K for a K-major operand, M / N for an MN-major one
+    if (a->lda < (a->a_major == SMB_MAJOR_K ? a->K : a->M) || a->ldb < (a->b_major == SMB_MAJOR_K ? a->K : a->N))
+        return fail(SMB_EINVAL, "smb_gemm: leading dimension smaller than the contiguous extent");
+    smb::GemmP p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->M; p.N = a->N; p.K = a->K; p.dtype = a->dtype; p.out_dtype = a->out_dtype;
+    p.a_mn = a->a_major; p.b_mn = a->b_major; p.epilogue = a->epilogue;
+    p.split_k = a->split_k < 1 ? 1 : a->split_k;
+    p.atomic = (p.split_k > 1 || a->accumulate) ? 1 : 0;
+    p.bias = a->bias; p.D = a->D; p.ldd = a->ldd;
+    cudaError_t e = smb::gemm_tc_launch(p, a->A, a->lda, a->B, a->ldb, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_gemm");
     return SMB_OK;
 }
 

@@ -216,9 +216,9 @@ static cudaError_t conv_launch_t(const ConvP &p, bool bwd, cudaStream_t st) {
 }
 
 cudaError_t conv1d_dispatch(const ConvP &p, int dtype, bool bwd, cudaStream_t st) {
-    {   // opt-in wide-run kernels for 16-bit activations (read per call: a tuning switch, not an API)
+    {   // 16-bit activations: 16 positions per thread (conv1d_v2.cu); SMB_CONV_V2=0 keeps 8 per thread (A/B switch, read per call)
         const char *v2 = getenv("SMB_CONV_V2");
-        if (dtype != 0 && v2 && v2[0] == '1') return conv1d_v2_dispatch(p, dtype, bwd, st);
+        if (dtype != 0 && !(v2 && v2[0] == '0')) return conv1d_v2_dispatch(p, dtype, bwd, st);
     }
     switch (dtype) {
         case 0: return conv_launch_t<float>(p, bwd, st);
@@ -241,9 +241,9 @@ static cudaError_t permute_launch_t(const void *src, void *dst, int64_t src_rs, 
 
 cudaError_t seq_permute_dispatch(const void *src, void *dst, int64_t src_rs, int64_t dst_rs, int rows, int L, int ns,
                                  int inverse, int accumulate, int dtype, cudaStream_t st) {
-    {   // opt-in 4-byte-access kernel for 16-bit activations (read per call: a tuning switch, not an API)
+    {   // 16-bit activations: 4-byte accesses (conv1d_v2.cu); SMB_PERMUTE_V2=0 keeps the 2-byte kernel (A/B switch, read per call)
         const char *v2 = getenv("SMB_PERMUTE_V2");
-        if (dtype != 0 && v2 && v2[0] == '1') {
+        if (dtype != 0 && !(v2 && v2[0] == '0')) {
             const cudaError_t e = seq_permute_v2_dispatch(src, dst, src_rs, dst_rs, rows, L, ns, inverse, accumulate, dtype, st);
             if (e != cudaErrorNotSupported) return e;
         }

@@ -750,8 +750,8 @@ static cudaError_t launch_bwd(const ScanP &p, cudaStream_t st) {
     // R1
     const int ctas = (p.n_work + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t sm1 = (size_t)kWarpsPerCta * (3 * kTile * kTile + kTile * N) * sizeof(float);
-    const char *r1v2 = getenv("SMB_RAGG_V2");                 // opt-in software-pipelined R1 for 16-bit activations (scan_bwd_v2.cu)
-    if (sizeof(T) == 2 && r1v2 && r1v2[0] == '1') {
+    const char *r1v2 = getenv("SMB_RAGG_V2");                 // software-pipelined R1 for 16-bit activations (scan_bwd_v2.cu); =0: A/B
+    if (sizeof(T) == 2 && !(r1v2 && r1v2[0] == '0')) {
         if ((e = scan_bwd_ragg_v2_dispatch(p, sizeof(T) == 2 && std::is_same<T, __half>::value ? 1 : 2, N, kHasZ, st)) != cudaSuccess) return e;
     } else {
         SMB_SET_SMEM_ONCE((scan_bwd_ragg_kernel<T, N, kHasZ>), sm1);
@@ -770,9 +770,9 @@ static cudaError_t launch_bwd(const ScanP &p, cudaStream_t st) {
         return cudaGetLastError();
     }
     // R3 (low-memory path; also used when the caller wants out_z recomputed)
-    {   // opt-in second-generation R3 (scan_bwd_r3v2.cu): same results, fewer instructions per update
+    {   // second-generation R3 (scan_bwd_r3v2.cu): same results, fewer instructions per update; SMB_R3_V2=0 keeps the first one (A/B)
         const char *r3v2 = getenv("SMB_R3_V2");
-        if (r3v2 && r3v2[0] == '1')
+        if (!(r3v2 && r3v2[0] == '0'))
             return scan_bwd_main_v2_dispatch(p, std::is_same<T, float>::value ? 0 : (std::is_same<T, __half>::value ? 1 : 2), N, kHasZ, st);
     }
     const size_t sm3 = (size_t)(2 * N + 2 * kBwdWarps) * kRowPad * sizeof(float);

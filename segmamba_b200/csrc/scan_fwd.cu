@@ -366,9 +366,12 @@ cudaError_t x_finalize_launch(const ScanP &p, int N, float *x, cudaStream_t st) 
 }
 
 cudaError_t scan_fwd_dispatch(const ScanP &p, int dtype, int N, bool has_z, float *x, cudaStream_t st) {
-    {   // opt-in software-pipelined kernels for 16-bit activations (read per call: a tuning switch, not an API)
+    {   // 16-bit activations: software-pipelined kernels, tiles staged by TMA (mode 2; falls back to cp.async staging, mode 1,
+        // when no tensor map can describe the operands).  SMB_FWD_V2=0 selects the single-buffered kernels below, =1 the
+        // cp.async staging -- A/B switches (profiles/r2a_microbench_ab.md), read per call.
         const char *v2 = getenv("SMB_FWD_V2");
-        if (dtype != 0 && v2 && (v2[0] == '1' || v2[0] == '2')) return scan_fwd_v2_dispatch(p, dtype, N, has_z, x, v2[0] - '0', st);
+        const int mode = (v2 && v2[0] >= '0' && v2[0] <= '2') ? v2[0] - '0' : 2;
+        if (dtype != 0 && mode) return scan_fwd_v2_dispatch(p, dtype, N, has_z, x, mode, st);
     }
     switch (dtype) {
         case 0: return launch_fwd_n<float>(p, N, has_z, x, st);

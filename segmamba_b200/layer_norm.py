@@ -15,9 +15,9 @@ from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
 
-# Validated against F.layer_norm on the CPU SIMT emulation of the kernel (tests/test_emu_kernels.py); it has not run on
-# hardware yet, so MambaLayer keeps nn.LayerNorm unless SMB_FUSED_LAYERNORM=1.
-ENABLED = os.environ.get("SMB_FUSED_LAYERNORM", "0") == "1"
+# Default on (hardware parity: tests/test_gpu_layernorm.py; step 98.4 -> 94.7 ms, profiles/r2a_bench_ab.md);
+# SMB_FUSED_LAYERNORM=0 keeps nn.LayerNorm for A/B runs.
+ENABLED = os.environ.get("SMB_FUSED_LAYERNORM", "1") != "0"
 
 
 def supported(x: torch.Tensor, normalized_dim: int) -> bool:

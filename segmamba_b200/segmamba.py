@@ -16,8 +16,6 @@ transpose copy each way, segmamba.py:69,74), and (iii) the fused instance-norm k
 """
 from __future__ import annotations
 
-import os
-
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -27,23 +25,6 @@ from .instance_norm import fused_instance_norm
 from .mamba_simple import Mamba
 
 _CL = torch.channels_last_3d
-
-# opt-in (SMB_PAD_CIN=1, until measured): the three convolutions that read the 4-channel input (stem 7^3, encoder1 3^3 and 1^3)
-# run as cuDNN's legacy sm80 indexed kernels because 4 bf16 channels are not a 16-byte vector
-# (profiles/r1_launches_train_step_v3_summary.txt: sm80_xmma_fprop/wgrad..., 3.3 ms of the step).  With the switch on, the input
-# is zero-padded to 8 channels once per forward and those convolutions pad their weight along C_in on the fly: the extra
-# channels contribute exact zeros, parameters and state_dict are untouched.
-PAD_CIN = os.environ.get("SMB_PAD_CIN", "0") == "1"
-
-
-def _conv_cin_padded(conv: nn.Conv3d, x):
-    """conv(x) where x may carry zero channels beyond conv.in_channels (see PAD_CIN)."""
-    extra = x.shape[1] - conv.in_channels
-    if extra == 0:
-        return conv(x)
-    w = F.pad(conv.weight, (0, 0, 0, 0, 0, 0, 0, extra))
-    return F.conv3d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
-
 
 class _Conv(nn.Sequential):
     """stand-in for monai Convolution(conv_only-like: act=None, norm=None): a Sequential with one child `conv`."""
@@ -75,10 +56,10 @@ class UnetResBlock(nn.Module):
 
     def forward(self, inp):
         # norm1/norm2/norm3/lrelu stay registered for structural parity; the math runs in the fused kernels
-        out = fused_instance_norm(_conv_cin_padded(self.conv1.conv, inp), "leaky_relu", 0.01)   # dynunet_block.py:100-102
+        out = fused_instance_norm(self.conv1.conv(inp), "leaky_relu", 0.01)   # dynunet_block.py:100-102
         out = self.conv2(out)
         if self.downsample:                                                               # :105-110
-            return fused_instance_norm(out, "leaky_relu", 0.01, add=_conv_cin_padded(self.conv3.conv, inp), add_norm=True)
+            return fused_instance_norm(out, "leaky_relu", 0.01, add=self.conv3.conv(inp), add_norm=True)
         return fused_instance_norm(out, "leaky_relu", 0.01, add=inp)
 
 
@@ -219,7 +200,7 @@ class MambaEncoder(nn.Module):
         outs = []
         for i in range(4):
             if i == 0:
-                x = _conv_cin_padded(self.downsample_layers[0][0], x)
+                x = self.downsample_layers[0][0](x)
             else:                                       # Sequential(InstanceNorm3d, Conv3d), segmamba.py:145-149
                 x = self.downsample_layers[i][1](fused_instance_norm(x))
             x = self.gscs[i](x)
@@ -266,10 +247,6 @@ class SegMamba(nn.Module):
         self.to(memory_format=_CL)
 
     def forward(self, x_in):
-        if PAD_CIN and x_in.shape[1] % 8 != 0:
-            if torch.is_autocast_enabled(x_in.device.type):          # one cast here instead of one per consumer
-                x_in = x_in.to(torch.get_autocast_dtype(x_in.device.type))
-            x_in = F.pad(x_in, (0, 0, 0, 0, 0, 0, 0, (-x_in.shape[1]) % 8))
         x_in = x_in.contiguous(memory_format=_CL)
         outs = self.vit(x_in)
         enc1 = self.encoder1(x_in)

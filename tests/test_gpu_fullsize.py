@@ -1,0 +1,119 @@
+"""BASELINE-size parity cases (they run in seconds on a B200):
+  * config 2: the default SegMamba on one 4x128^3 patch, fp32, eval -- native module vs the reference's
+    op sequence (oracle.segmamba_forward: NCDHW, flips / stack / rearrange copies, ATen norms) running on the reference's OWN CUDA
+    kernels compiled for sm_100a (oracle/_ref, built by oracle/build_ref.py), same state_dict;
+  * fused instance norm at the largest activation of the model (2, 48, 128^3) against fp32 torch;
+  * one bf16 training step at full size: loss and global gradient norm of the native module against the reference-kernel step,
+    and the two native backward paths against each other."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_REF_SO = os.path.join(ROOT, "oracle", "_ref", "selective_scan_cuda.so")
+needs_ref = pytest.mark.skipif(not os.path.exists(_REF_SO), reason="oracle/_ref not built (python oracle/build_ref.py)")
+
+
+def _ref_tools():
+    spec = importlib.util.spec_from_file_location("ref_equivalent_step", os.path.join(ROOT, "tools", "ref_equivalent_step.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture
+def exact_fp32():
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+@needs_ref
+def test_config2_default_model_128_fp32_vs_reference_cuda(exact_fp32):
+    from oracle import oracle as orc
+    from segmamba_b200.segmamba import SegMamba
+    _ref_tools().bind_reference_kernels(orc)
+    torch.manual_seed(0)
+    m = SegMamba(in_chans=4, out_chans=4, depths=[2, 2, 2, 2], feat_size=[48, 96, 192, 384]).cuda().eval()
+    sd = {k: v.detach().clone().contiguous() for k, v in m.state_dict().items()}
+    x = torch.rand(1, 4, 128, 128, 128, device="cuda")                      # 0_inference.py:6
+    with torch.no_grad():
+        out = m(x)
+        ref = orc.segmamba_forward(sd, x)
+    assert out.shape == (1, 4, 128, 128, 128)
+    assert_close(out, ref, 1e-3, "config 2 logits vs the reference op sequence on the reference CUDA kernels")
+
+
+@pytest.mark.parametrize("mode", ["plain", "residual", "two_norms"])
+def test_fused_instance_norm_largest_activation(mode):
+    from segmamba_b200.instance_norm import fused_instance_norm
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    shape = (2, 48, 128, 128, 128)
+    x = (torch.randn(shape, device="cuda") * 2 + 0.5).bfloat16().contiguous(memory_format=torch.channels_last_3d).requires_grad_()
+    x2 = torch.randn(shape, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last_3d).requires_grad_()
+    dy = torch.randn(shape, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last_3d)
+    if mode == "plain":
+        y = fused_instance_norm(x, "leaky_relu", 0.01)
+        ins = [x]
+    elif mode == "residual":
+        y = fused_instance_norm(x, "leaky_relu", 0.01, add=x2)
+        ins = [x, x2]
+    else:
+        y = fused_instance_norm(x, "leaky_relu", 0.01, add=x2, add_norm=True)
+        ins = [x, x2]
+    g = torch.autograd.grad(y, ins, dy)
+    xr, x2r = x.detach().float().requires_grad_(), x2.detach().float().requires_grad_()
+    t = F.instance_norm(xr, eps=1e-5)
+    if mode == "residual":
+        t = t + x2r
+    elif mode == "two_norms":
+        t = t + F.instance_norm(x2r, eps=1e-5)
+    yr = F.leaky_relu(t, 0.01)
+    gr = torch.autograd.grad(yr, [xr, x2r][:len(ins)], dy.float())
+    assert_close(y, yr, 1e-2, "y")
+    for a, b, n in zip(g, gr, ("dx", "dx2")):
+        assert_close(a, b, 2e-2, n)
+
+
+def _step_loss_and_gradnorm(forward, params, x, y):
+    for p in params:
+        p.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = torch.nn.functional.cross_entropy(forward(x).float(), y)
+    loss.backward()
+    gn = torch.nn.utils.clip_grad_norm_(params, 1e9)
+    return float(loss), float(gn)
+
+
+@needs_ref
+def test_full_size_bf16_training_step_vs_reference_kernels():
+    from oracle import oracle as orc
+    from segmamba_b200 import selective_scan_cuda as ssc
+    from segmamba_b200.segmamba import SegMamba
+    _ref_tools().bind_reference_kernels(orc)
+    torch.manual_seed(0)
+    m = SegMamba(in_chans=4, out_chans=4, depths=[2, 2, 2, 2], feat_size=[48, 96, 192, 384]).cuda().train()
+    x = torch.rand(2, 4, 128, 128, 128, device="cuda")
+    y = torch.randint(0, 4, (2, 128, 128, 128), device="cuda")
+    params = list(m.parameters())
+    la, ga = _step_loss_and_gradnorm(m, params, x, y)
+    old = ssc.LOW_MEMORY_BWD
+    try:
+        ssc.LOW_MEMORY_BWD = not old
+        lb, gb = _step_loss_and_gradnorm(m, params, x, y)
+    finally:
+        ssc.LOW_MEMORY_BWD = old
+    rp = {k: torch.nn.Parameter(v.detach().clone().contiguous()) for k, v in m.state_dict().items()}
+    lr, gr = _step_loss_and_gradnorm(lambda t: orc.segmamba_forward(rp, t), list(rp.values()), x, y)
+    print(f"full-size bf16 step: loss native {la:.5f} / other backward path {lb:.5f} / reference kernels {lr:.5f}; "
+          f"grad norm {ga:.4f} / {gb:.4f} / {gr:.4f}")
+    assert abs(la - lb) <= 1e-3 * abs(la) and abs(ga - gb) <= 1e-2 * ga
+    assert abs(la - lr) <= 1e-2 * abs(lr), (la, lr)
+    assert abs(ga - gr) <= 3e-2 * gr, (ga, gr)

@@ -1,5 +1,6 @@
-"""Every alternative scan kernel that a build/run switch can select (SMB_FWD_V2 = 1: cp.async-pipelined forward, 2: TMA-staged
-forward; SMB_RAGG_V2: pipelined reverse aggregate; SMB_R3_V2: second-generation main backward pass) against the CPU ORACLE --
+"""Every scan kernel a run-time switch can select (SMB_FWD_V2 = 2: TMA-staged forward [default], 1: cp.async-pipelined, 0:
+single-buffered; SMB_RAGG_V2: pipelined reverse aggregate; SMB_R3_V2: second-generation main backward pass; SMB_SEG_MIN: shortest
+segment) against the CPU ORACLE --
 not against the default kernels -- at a ragged small size (partial tiles, partial channel octets, scalar tails) and at the
 BASELINE stage-0 size (batch 1, D=96, L=262144, N=16: every segment / carry / vector-reduction path at full length).
 A switch whose kernel fails here is removed from the tree, not masked."""
@@ -11,15 +12,18 @@ from util import GRAD_TOL, TOL, assert_close, rand_scan_inputs
 
 pytestmark = pytest.mark.gpu
 
+# "default" = what ships (TMA-staged forward, pipelined R1, second-generation R3 for 16-bit activations; the single-buffered
+# kernels for fp32); the other entries select the A/B alternatives one at a time, "legacy" all of them
 VARIANTS = {
     "default": {},
     "fwd_cp_async": {"SMB_FWD_V2": "1"},
-    "fwd_tma": {"SMB_FWD_V2": "2"},
-    "ragg_v2": {"SMB_RAGG_V2": "1"},
-    "r3_v2": {"SMB_R3_V2": "1"},
-    "all": {"SMB_FWD_V2": "2", "SMB_RAGG_V2": "1", "SMB_R3_V2": "1"},
+    "fwd_single_buffered": {"SMB_FWD_V2": "0"},
+    "ragg_v1": {"SMB_RAGG_V2": "0"},
+    "r3_v1": {"SMB_R3_V2": "0"},
+    "seg256": {"SMB_SEG_MIN": "256"},
+    "legacy": {"SMB_FWD_V2": "0", "SMB_RAGG_V2": "0", "SMB_R3_V2": "0", "SMB_SEG_MIN": "256"},
 }
-ALL_SWITCHES = ("SMB_FWD_V2", "SMB_RAGG_V2", "SMB_R3_V2")
+ALL_SWITCHES = ("SMB_FWD_V2", "SMB_RAGG_V2", "SMB_R3_V2", "SMB_SEG_MIN")
 _oracle_cache = {}
 
 
@@ -33,7 +37,10 @@ def _oracle_cached(key, d, flip):
 def _run(d, direction, monkeypatch, env):
     from segmamba_b200 import selective_scan_cuda as ssc
     for k in ALL_SWITCHES:
-        monkeypatch.setenv(k, env.get(k, "0"))
+        if k in env:
+            monkeypatch.setenv(k, env[k])
+        else:
+            monkeypatch.delenv(k, raising=False)
     B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
     out, x, out_z, hst = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, direction=direction,
                                     want_out=True, want_x=True, want_hstates=True)
@@ -49,8 +56,8 @@ def _run(d, direction, monkeypatch, env):
 @pytest.mark.parametrize("shape", [(2, 44, 5003), (1, 96, 262144)], ids=["ragged", "stage0"])
 def test_scan_variant_vs_oracle(monkeypatch, variant, dtype, direction, shape):
     env = VARIANTS[variant]
-    if dtype == torch.float32 and variant in ("fwd_cp_async", "fwd_tma", "ragg_v2"):
-        pytest.skip("16-bit activation kernels")
+    if dtype == torch.float32 and variant in ("fwd_cp_async", "fwd_single_buffered", "ragg_v1"):
+        pytest.skip("switch only affects 16-bit activations")
     if shape[2] > 100000 and dtype == torch.float16:
         pytest.skip("full size: bf16 and fp32 only")
     batch, dim, L = shape
