@@ -94,7 +94,13 @@ typedef struct smb_scan_fwd_args {
     int64_t B_bs, B_gs, B_ns, B_ls, C_bs, C_gs, C_ns, C_ls;
     void *workspace;
     size_t workspace_bytes;  /* >= smb_scan_fwd_workspace_bytes(...) */
+    float *hdense;   /* smb_scan_dense_floats(...) floats or NULL: the state entering every 8th scan position, laid out per
+                        (batch, channel octet, block of 8 positions)[channel in octet][state]; feed to smb_scan_bwd, whose main
+                        pass then needs neither a forward-state recompute nor a warp scan per state */
 } smb_scan_fwd_args;
+
+/* floats of the dense checkpoint arrays (hdense of smb_scan_fwd / smb_scan_bwd, mdense of smb_scan_bwd) */
+SMB_API size_t smb_scan_dense_floats(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t n_groups);
 
 SMB_API size_t smb_scan_fwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate);
 SMB_API int smb_scan_fwd(const smb_scan_fwd_args *args, void *cuda_stream);
@@ -124,6 +130,10 @@ typedef struct smb_scan_bwd_args {
     int64_t B_bs, B_gs, B_ns, B_ls, C_bs, C_gs, C_ns, C_ls;
     void *workspace;
     size_t workspace_bytes;     /* >= smb_scan_bwd_workspace_bytes(...) */
+    const float *hdense;        /* dense forward checkpoints from smb_scan_fwd, or NULL.  With hdense (and low_memory != 0) the
+                                   main pass is scan-free: every lane starts its 8-position run from a saved state and a saved
+                                   local adjoint (mdense, written by the reverse-aggregate pass) */
+    float *mdense;              /* scratch of smb_scan_dense_floats(...) floats, required iff hdense != NULL */
 } smb_scan_bwd_args;
 
 SMB_API size_t smb_scan_bwd_workspace_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t dtype,

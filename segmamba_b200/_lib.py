@@ -29,7 +29,7 @@ class ScanFwdArgs(ctypes.Structure):
         + [(n, _vp) for n in ("u", "delta", "z", "A", "D", "delta_bias", "B", "C", "out", "out_z", "x", "hstates")]
         + [(n, _i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "z_bs", "z_ds", "out_bs", "out_ds", "out_z_bs",
                                "out_z_ds", "B_bs", "B_gs", "B_ns", "B_ls", "C_bs", "C_gs", "C_ns", "C_ls")]
-        + [("workspace", _vp), ("workspace_bytes", _sz)]
+        + [("workspace", _vp), ("workspace_bytes", _sz), ("hdense", _vp)]
     )
 
 
@@ -42,7 +42,7 @@ class ScanBwdArgs(ctypes.Structure):
         + [(n, _i64) for n in ("u_bs", "u_ds", "delta_bs", "delta_ds", "z_bs", "z_ds", "dout_bs", "dout_ds",
                                "du_bs", "du_ds", "ddelta_bs", "ddelta_ds", "dz_bs", "dz_ds", "out_z_bs", "out_z_ds",
                                "B_bs", "B_gs", "B_ns", "B_ls", "C_bs", "C_gs", "C_ns", "C_ls")]
-        + [("workspace", _vp), ("workspace_bytes", _sz)]
+        + [("workspace", _vp), ("workspace_bytes", _sz), ("hdense", _vp), ("mdense", _vp)]
     )
 
 
@@ -108,6 +108,7 @@ EXPORTS = {
     "smb_last_error": (ctypes.c_char_p, []),
     "smb_launch_count": (ctypes.c_uint64, []),
     "smb_scan_fwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "smb_scan_dense_floats": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "smb_scan_fwd": (ctypes.c_int, [ctypes.POINTER(ScanFwdArgs), _vp]),
     "smb_scan_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "smb_scan_bwd": (ctypes.c_int, [ctypes.POINTER(ScanBwdArgs), _vp]),

@@ -90,6 +90,12 @@ SMB_API size_t smb_scan_fwd_workspace_bytes(int32_t batch, int32_t dim, int32_t 
     return sizeof(float) * (4 * seg_floats + plmax.ck_floats);
 }
 
+SMB_API size_t smb_scan_dense_floats(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t n_groups) {
+    if (batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0 || n_groups <= 0 || dim % n_groups) return 0;
+    const size_t nck = (size_t)(seqlen + smb::kCkpt - 1) / smb::kCkpt;
+    return (size_t)batch * smb::dense_octs(dim / n_groups, n_groups) * nck * 32 * 8 * dstate;
+}
+
 SMB_API int smb_scan_fwd(const smb_scan_fwd_args *a, void *cuda_stream) {
     if (!a) return fail(SMB_EINVAL, "smb_scan_fwd: null args");
     int rc = check_common(a->batch, a->dim, a->seqlen, a->dstate, a->n_groups, a->dtype, "smb_scan_fwd");
@@ -122,6 +128,7 @@ SMB_API int smb_scan_fwd(const smb_scan_fwd_args *a, void *cuda_stream) {
     const size_t segf = seg_floats_max(a->batch, a->dim, a->seqlen, N);
     p.P = ws; p.H = ws + segf; p.hin = ws + 2 * segf; p.cumP = ws + 3 * segf;
     p.hstates = a->hstates ? a->hstates : (a->x ? ws + 4 * segf : nullptr);
+    p.hd = a->hdense;
     cudaError_t e = smb::scan_fwd_dispatch(p, a->dtype, N, a->z != nullptr, a->x, (cudaStream_t)cuda_stream);
     if (e != cudaSuccess) return cuda_fail(e, "smb_scan_fwd");
     return SMB_OK;
@@ -148,6 +155,7 @@ SMB_API int smb_scan_bwd(const smb_scan_bwd_args *a, void *cuda_stream) {
     if (!a->du || !a->ddelta || !a->dA || !a->dB || !a->dC) return fail(SMB_EINVAL, "smb_scan_bwd: du, ddelta, dA, dB, dC are required");
     if (a->z && !a->dz) return fail(SMB_EINVAL, "smb_scan_bwd: dz is required when z is given");
     if (a->B_ls != 1 || a->C_ls != 1) return fail(SMB_EUNSUPPORTED, "smb_scan_bwd: B and C must have unit stride along L");
+    if (a->hdense && !a->mdense) return fail(SMB_EINVAL, "smb_scan_bwd: mdense scratch is required with hdense");
     const size_t need = smb_scan_bwd_workspace_bytes(a->batch, a->dim, a->seqlen, a->dstate, a->dtype, a->low_memory);
     if (!a->workspace || a->workspace_bytes < need)
         return fail(SMB_EWORKSPACE, "smb_scan_bwd: workspace of %zu bytes required, got %zu", need, a->workspace_bytes);
@@ -181,7 +189,12 @@ SMB_API int smb_scan_bwd(const smb_scan_bwd_args *a, void *cuda_stream) {
     p.stash = a->low_memory ? nullptr : reinterpret_cast<void *>(align_up(reinterpret_cast<size_t>(ws + 6 * ckf), 256));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     cudaError_t e;
-    if (a->hstates) {
+    if (a->hdense && a->low_memory) {                     // scan-free main pass: no chunk states needed at all
+        p.hd = const_cast<float *>(a->hdense);
+        p.md = a->mdense;
+        p.hs = a->hstates ? a->hstates : p.hin;
+        p.hs_bs = (int64_t)(pl.nck + (a->hstates ? 1 : 0)) * N * a->dim;
+    } else if (a->hstates) {
         p.hs = a->hstates;
         p.hs_bs = (int64_t)(pl.nck + 1) * N * a->dim;
     } else {

@@ -369,6 +369,7 @@ cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, i
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
     if (p.BN <= 0) p.BN = gemm_pick_bn(p.N);
+    if (p.out_dtype == 0 && p.BN > 128) p.BN = 128;      // fp32 staging tile: 128 x (BN * 4 + 16) bytes must leave room for >= 2 stages
     const int BN = p.BN;
     const size_t osz = p.out_dtype == 0 ? 4 : 2;
     const size_t b_tile = p.b_mn ? (size_t)((BN + 63) / 64) * 8192 : (size_t)BN * 128;

@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) scan_bwd_ragg_kernel(const 
             const float dd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
             const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
             ragg_block<N, 7>(blkC, gg, dd, A2, mu, sumdt);
+            const int blk = (j0 + 4 * c0) >> 3;            // block just finished; its left neighbour starts its adjoint from mu
+            if (p.md && active && (blk & 31)) dense_store<N>(p.md + dense_slot(p, wi.b, wi.g, d, blk - 1, N), mu);
         }
         __syncwarp();
     }

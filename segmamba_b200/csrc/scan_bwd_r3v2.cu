@@ -106,6 +106,9 @@ __device__ __forceinline__ float from_right(float v, float edge, int lane) {
 // ---- one state of one channel: everything that needs h and lambda at the same (position, state) ----
 // Writes this lane's 8 dB / dC terms into the warp's slab rows and its dA partial into sda[n]; accumulates the per-position
 // sums over states (lambda B, A lambda (h - b), C h) in place.
+// kDense (scan-free): h_in / m_in are THIS lane's own values -- the saved state entering its run and the adjoint entering it
+// from the right -- so the lane aggregates, both Kogge-Stone scans and the neighbour exchanges disappear.
+template <bool kDense>
 __device__ __forceinline__ void r3_state(const float *__restrict__ rowB, const float *__restrict__ rowC, float A2n, float h_in,
                                          float m_in, float sumdt, int lane, const float2 (&dt2)[kRun / 2],
                                          const float2 (&dtu2)[kRun / 2], const float2 (&g2)[kRun / 2], float2 (&sLB2)[kRun / 2],
@@ -127,6 +130,21 @@ __device__ __forceinline__ void r3_state(const float *__restrict__ rowB, const f
         gc2[j] = __fmul2_rn(g2[j], Cv2[j]);
         agc2[j] = __fmul2_rn(a2[j], gc2[j]);
     }
+    if constexpr (kDense) {
+        float h = h_in;
+#pragma unroll
+        for (int j = 0; j < kRun / 2; ++j) {
+            h = fmaf(a2[j].x, h, bb2[j].x); hs2[j].x = h;
+            h = fmaf(a2[j].y, h, bb2[j].y); hs2[j].y = h;
+        }
+        float m = m_in;                                    // mu entering this run from the right
+#pragma unroll
+        for (int j = kRun / 2 - 1; j >= 0; --j) {
+            const float my = m; m = fmaf(a2[j].y, m, agc2[j].y);
+            const float mx = m; m = fmaf(a2[j].x, m, agc2[j].x);
+            lam2[j] = __fadd2_rn(gc2[j], f2(mx, my));      // lambda_i = g_i C_i + mu_{i+1}
+        }
+    } else {
     const float Aagg = ex2(A2n * sumdt);               // product of the run's eight decays
     // ---- forward: lane aggregate, inclusive scan (h_in folded into lane 0), state entering the run, re-run ----
     float Hagg = 0.f;
@@ -167,6 +185,7 @@ __device__ __forceinline__ void r3_state(const float *__restrict__ rowB, const f
             lam2[j] = __fadd2_rn(gc2[j], f2(mx, my));  // lambda_i = g_i C_i + mu_{i+1}
         }
     }
+    }   // !kDense
     // ---- element-wise gradient terms, two positions per instruction ----
     float2 dA2 = f2(0.f, 0.f), dB2[kRun / 2], dC2[kRun / 2];
 #pragma unroll
@@ -194,7 +213,7 @@ template <int N> struct R3Smem {
     static constexpr size_t kBytes = sizeof(float) * (size_t)(kBC + kSlab + kDa);
 };
 
-template <typename T, int N, bool kHasZ>
+template <typename T, int N, bool kHasZ, bool kDense>
 __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP p) {
     extern __shared__ __align__(16) float smem[];
     float *sB = smem;                                   // [N][kPad]
@@ -285,8 +304,19 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
     float A2_l = 0.f, hin_l = 0.f, min_l = 0.f;
     if (active && lane < N) {
         A2_l = p.A[(int64_t)d * N + lane] * kLog2e;
-        hin_l = p.hs[(int64_t)b * p.hs_bs + ((int64_t)chunk * N + lane) * p.dim + d];
+        if (!kDense) hin_l = p.hs[(int64_t)b * p.hs_bs + ((int64_t)chunk * N + lane) * p.dim + d];
         min_l = p.Min[(((int64_t)b * p.nck + chunk) * N + lane) * p.dim + d];
+    }
+    // scan-free path: this lane's own checkpoints (state entering its run; local adjoint entering it from the right, which R1
+    // computed with a zero adjoint at the chunk end -- the carried adjoint Min comes in through the decay product below)
+    const float *hdp = nullptr, *mdp = nullptr;
+    bool use_h = false, use_m = false;
+    if (kDense) {
+        const int64_t slot = dense_slot(p, b, g, active ? d : d0, chunk * 32 + lane, N);
+        hdp = p.hd + slot;
+        mdp = p.md + slot;
+        use_h = active && jl < L;                       // blocks past the end were never written
+        use_m = use_h && lane < 31 && jl + kRun < L;    // the chunk's / sequence's last block starts from Min alone
     }
     float2 dt2[kRun / 2], dtu2[kRun / 2], g2[kRun / 2], sLB2[kRun / 2], sAq2[kRun / 2], yy2[kRun / 2];
     float sumdt = 0.f;
@@ -297,6 +327,17 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         g2[j] = f2(gg[2 * j], gg[2 * j + 1]);
         sLB2[j] = f2(0.f, 0.f); sAq2[j] = f2(0.f, 0.f); yy2[j] = f2(0.f, 0.f);
         sumdt += dt[2 * j] + dt[2 * j + 1];
+    }
+    // sum of dt over the lanes to the right (exclusive suffix): the decay from the chunk end back to this run is ex2(A * suffix)
+    float suffix = 0.f;
+    if (kDense) {
+        float inc = sumdt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_down_sync(0xffffffffu, inc, o);
+            if (lane + o < 32) inc += t;
+        }
+        suffix = inc - sumdt;
     }
 
     // reduction role of this thread: (state of the round, tensor) x 4 consecutive positions
@@ -314,8 +355,16 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         const float hia = __shfl_sync(0xffffffffu, hin_l, n), hib = __shfl_sync(0xffffffffu, hin_l, n + 1);
         const float mia = __shfl_sync(0xffffffffu, min_l, n), mib = __shfl_sync(0xffffffffu, min_l, n + 1);
         if (active) {
-            r3_state(rowB, rowC, A2a, hia, mia, sumdt, lane, dt2, dtu2, g2, sLB2, sAq2, yy2, myB0, myC0, sda + n);
-            r3_state(rowB + kPad, rowC + kPad, A2b, hib, mib, sumdt, lane, dt2, dtu2, g2, sLB2, sAq2, yy2, myB1, myC1, sda + n + 1);
+            if constexpr (kDense) {
+                const float2 hv = use_h ? *reinterpret_cast<const float2 *>(hdp + n) : f2(0.f, 0.f);
+                const float2 mv = use_m ? *reinterpret_cast<const float2 *>(mdp + n) : f2(0.f, 0.f);
+                const float ma = fmaf(ex2(A2a * suffix), mia, mv.x), mb = fmaf(ex2(A2b * suffix), mib, mv.y);
+                r3_state<true>(rowB, rowC, A2a, hv.x, ma, sumdt, lane, dt2, dtu2, g2, sLB2, sAq2, yy2, myB0, myC0, sda + n);
+                r3_state<true>(rowB + kPad, rowC + kPad, A2b, hv.y, mb, sumdt, lane, dt2, dtu2, g2, sLB2, sAq2, yy2, myB1, myC1, sda + n + 1);
+            } else {
+                r3_state<false>(rowB, rowC, A2a, hia, mia, sumdt, lane, dt2, dtu2, g2, sLB2, sAq2, yy2, myB0, myC0, sda + n);
+                r3_state<false>(rowB + kPad, rowC + kPad, A2b, hib, mib, sumdt, lane, dt2, dtu2, g2, sLB2, sAq2, yy2, myB1, myC1, sda + n + 1);
+            }
         }
         rowB += 2 * kPad; rowC += 2 * kPad;
         __syncthreads();
@@ -417,10 +466,15 @@ template <typename T, int N, bool kHasZ>
 cudaError_t launch_main2(const ScanP &p, cudaStream_t st) {
     const size_t sm = R3Smem<N>::kBytes;
     cudaError_t e;
-    SMB_SET_SMEM_ONCE((scan_bwd_main2_kernel<T, N, kHasZ>), sm);
     const int octs = ((p.dim_per_group + kW - 1) / kW) * p.G;
     dim3 grid(p.nck, octs, p.batch);
-    scan_bwd_main2_kernel<T, N, kHasZ><<<grid, kW * 32, sm, st>>>(p); count_launch();
+    if (p.hd && p.md) {
+        SMB_SET_SMEM_ONCE((scan_bwd_main2_kernel<T, N, kHasZ, true>), sm);
+        scan_bwd_main2_kernel<T, N, kHasZ, true><<<grid, kW * 32, sm, st>>>(p); count_launch();
+    } else {
+        SMB_SET_SMEM_ONCE((scan_bwd_main2_kernel<T, N, kHasZ, false>), sm);
+        scan_bwd_main2_kernel<T, N, kHasZ, false><<<grid, kW * 32, sm, st>>>(p); count_launch();
+    }
     return cudaGetLastError();
 }
 template <typename T>

@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_bwd_ragg2_kernel(co
                 for (int e = 0; e < 8; ++e) gg[e] *= zz[e] * sigmoidf(zz[e]);
             }
             ragg_block<N, 7>(s_C + 8 * u8 * N, gg, dd, A2, mu, sumdt);
+            const int blk = (j0 >> 3) + u8;                      // block just finished; its left neighbour starts from mu
+            if (p.md && active && (blk & 31)) dense_store<N>(p.md + dense_slot(p, wi.b, wi.g, d, blk - 1, N), mu);
         }
         __syncwarp();
         pending = next_async;

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, SMB_FWD_MAIN_MINB) scan_fwd
             const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w};
             const float dd[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
             float yy[8];
+            if (p.hd && active) dense_store<N>(p.hd + dense_slot(p, wi.b, wi.g, d, (j0 + 4 * c0) >> 3, N), h);
             main_block<N, 0>(blkB, blkC, uu, dd, Dv, A2, h, yy);
             if (kHasZ) {
                 const float4 za = tile_read4(s_z, lane, c0), zb = tile_read4(s_z, lane, c0 + 1);   // already silu(z)

@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) scan_fwd_main2_kernel(co
                 read_unit<T, kRev>(t_d, lane, u8, dd);
             }
             unit_dt(dd, bias, p.softplus, 8 * u8, nvalid);
+            if (p.hd && active) dense_store<N>(p.hd + dense_slot(p, wi.b, wi.g, d, (j0 >> 3) + u8, N), h);
             main_block<N, 0>(s_B + 8 * u8 * N, s_C + 8 * u8 * N, uu, dd, Dv, A2, h, yy);
             if (kHasZ) {
                 float zz[8];

@@ -38,7 +38,25 @@ struct ScanP {
     float *Pb, *Mloc, *Min;                        // (batch, nck, N, dim) reverse aggregates / carried adjoints
     void *stash;                                   // (batch, Lpad, N/2, dim) state pairs (bf16x2 or float2), or nullptr
     int Lpad;
+    // dense checkpoints (every 8th scan position), see dense_slot(): hd = forward state entering a block (written by the
+    // forward main pass, read by R3), md = local adjoint entering a block from the right (written by R1, read by R3)
+    float *hd, *md;
 };
+
+// Dense checkpoint layout, chosen for the reader: R3's CTA = (256-position chunk, channel octet) finds its 32 blocks x 8
+// channels x N states in one contiguous run; the writers (lane == channel) store N consecutive floats per lane.
+//   slot(b, octet, blk, w) = (((b * n_oct + octet) * (nck * 32) + blk) * 8 + w) * N,   octet / w from the channel's index in its group
+__host__ __device__ __forceinline__ int dense_octs(int dim_per_group, int G) { return ((dim_per_group + 7) >> 3) * G; }
+__device__ __forceinline__ int64_t dense_slot(const ScanP &p, int b, int g, int d, int blk, int N) {
+    const int dg = d - g * p.dim_per_group;
+    const int opg = (p.dim_per_group + 7) >> 3;
+    return ((((int64_t)b * (opg * p.G) + g * opg + (dg >> 3)) * ((int64_t)p.nck * 32) + blk) * 8 + (dg & 7)) * N;
+}
+template <int N>
+__device__ __forceinline__ void dense_store(float *dst, const float2 (&v)[N / 2]) {
+#pragma unroll
+    for (int k = 0; k < N / 4; ++k) *reinterpret_cast<float4 *>(dst + 4 * k) = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
+}
 
 struct WorkItem {
     int b, seg, g, d0, nrows;

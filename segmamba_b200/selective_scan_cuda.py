@@ -61,9 +61,16 @@ def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+# Dense checkpoints (the state entering every 8th scan position, 8 bytes per position and channel): with them the backward's
+# main pass starts every 8-position run from a saved state and a saved local adjoint instead of linking the runs with two
+# 5-step warp scans per state.  DENSE_STATES=False keeps the 256-position checkpoints only (A/B; both paths are parity-tested).
+DENSE_STATES = True
+
+
 def fwd_ex(u, delta, A, B, C, D_=None, z_=None, delta_bias_=None, delta_softplus=False, *, direction=0,
-           want_out=True, want_x=True, want_hstates=False):
-    """returns (out | None, x | None, out_z | None, hstates | None)."""
+           want_out=True, want_x=True, want_hstates=False, want_hdense=False):
+    """returns (out | None, x | None, out_z | None, hstates | None) and, with want_hdense, a fifth entry: the dense
+    checkpoints (or None when DENSE_STATES is off)."""
     batch, dim, L, N, G, B, C = _validate(u, delta, A, B, C, D_, z_, delta_bias_)
     A = A.contiguous()
     dev = u.device
@@ -75,6 +82,9 @@ def fwd_ex(u, delta, A, B, C, D_=None, z_=None, delta_bias_=None, delta_softplus
         nck = (L + CKPT - 1) // CKPT
         hst = torch.empty(batch, nck + 1, N, dim, dtype=torch.float32, device=dev) if want_hstates else None
         l = _lib.lib()
+        hdense = None
+        if want_hdense and DENSE_STATES:
+            hdense = torch.empty(l.smb_scan_dense_floats(batch, dim, L, N, G), dtype=torch.float32, device=dev)
         wsb = l.smb_scan_fwd_workspace_bytes(batch, dim, L, N)
         ws = _ws(wsb, dev)
         a = _lib.ScanFwdArgs()
@@ -96,8 +106,11 @@ def fwd_ex(u, delta, A, B, C, D_=None, z_=None, delta_bias_=None, delta_softplus
         a.B_bs, a.B_gs, a.B_ns, a.B_ls = B.stride(0), B.stride(1), B.stride(2), B.stride(3)
         a.C_bs, a.C_gs, a.C_ns, a.C_ls = C.stride(0), C.stride(1), C.stride(2), C.stride(3)
         a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
+        a.hdense = _lib.ptr(hdense)
         sp = _lib.stream_ptr(dev)
         _lib.call("scan_fwd", (batch, dim, L, N, u.element_size(), has_z, out is not None), lambda: l.smb_scan_fwd(ctypes.byref(a), sp), dev)
+    if want_hdense:
+        return out, x, out_z, hst, hdense
     return out, x, out_z, hst
 
 
@@ -112,7 +125,7 @@ LOW_MEMORY_BWD = True      # True: chunk-parallel recompute backward (small work
 
 
 def bwd_ex(u, delta, A, B, C, D_, z_, delta_bias_, dout, dz_=None, delta_softplus=False, recompute_out_z=False, *,
-           direction=0, hstates=None, low_memory=None):
+           direction=0, hstates=None, hdense=None, low_memory=None):
     """returns (du, ddelta, dA, dB(fp32), dC(fp32), dD, ddelta_bias, dz | None, out_z | None)."""
     batch, dim, L, N, G, B, C = _validate(u, delta, A, B, C, D_, z_, delta_bias_)
     _lib.require_cuda(dout)
@@ -153,6 +166,10 @@ def bwd_ex(u, delta, A, B, C, D_, z_, delta_bias_, dout, dz_=None, delta_softplu
         a.A, a.D, a.delta_bias = _lib.ptr(A), _lib.ptr(D_), _lib.ptr(delta_bias_)
         a.B, a.C, a.dout = _lib.ptr(B), _lib.ptr(C), _lib.ptr(dout)
         a.hstates = _lib.ptr(hstates)
+        mdense = None
+        if hdense is not None and low:
+            mdense = torch.empty_like(hdense)
+            a.hdense, a.mdense = _lib.ptr(hdense), _lib.ptr(mdense)
         a.du, a.ddelta, a.dz, a.out_z = _lib.ptr(du), _lib.ptr(ddelta), _lib.ptr(dz), _lib.ptr(out_z)
         a.dA, a.dB, a.dC, a.dD, a.ddelta_bias = _lib.ptr(dA), _lib.ptr(dB), _lib.ptr(dC), _lib.ptr(dD), _lib.ptr(dbias)
         a.u_bs, a.u_ds = u.stride(0), u.stride(1)
@@ -169,7 +186,7 @@ def bwd_ex(u, delta, A, B, C, D_, z_, delta_bias_, dout, dz_=None, delta_softplu
         a.C_bs, a.C_gs, a.C_ns, a.C_ls = C.stride(0), C.stride(1), C.stride(2), C.stride(3)
         a.workspace, a.workspace_bytes = ws.data_ptr(), wsb
         sp = _lib.stream_ptr(dev)
-        _lib.call("scan_bwd", (batch, dim, L, N, u.element_size(), has_z, hstates is not None, low), lambda: l.smb_scan_bwd(ctypes.byref(a), sp), dev)
+        _lib.call("scan_bwd", (batch, dim, L, N, u.element_size(), has_z, hstates is not None, low + (1 if mdense is not None else 0)), lambda: l.smb_scan_bwd(ctypes.byref(a), sp), dev)
     return du, ddelta, dA, dB, dC, dD, dbias, dz, out_z
 
 

@@ -51,11 +51,11 @@ class SelectiveScanFn(torch.autograd.Function):
             B = B.unsqueeze(1)
         if ctx.squeeze_C:
             C = C.unsqueeze(1)
-        out, x, out_z, hst = selective_scan_cuda.fwd_ex(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
-                                                        want_out=z is None, want_x=return_last_state, want_hstates=True)
+        out, x, out_z, hst, hd = selective_scan_cuda.fwd_ex(u, delta, A, B, C, D, z, delta_bias, delta_softplus, want_out=z is None,
+                                                            want_x=return_last_state, want_hstates=True, want_hdense=True)
         ctx.delta_softplus = delta_softplus
         ctx.has_z = z is not None
-        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, hst)
+        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, hst, hd)
         res = out_z if ctx.has_z else out
         if not return_last_state:
             return res
@@ -64,11 +64,11 @@ class SelectiveScanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, *args):
-        u, delta, A, B, C, D, z, delta_bias, hst = ctx.saved_tensors
+        u, delta, A, B, C, D, z, delta_bias, hst, hd = ctx.saved_tensors
         if dout.stride(-1) != 1:
             dout = dout.contiguous()
         du, ddelta, dA, dB, dC, dD, ddelta_bias, dz, _ = selective_scan_cuda.bwd_ex(
-            u, delta, A, B, C, D, z, delta_bias, dout, None, ctx.delta_softplus, False, hstates=hst)
+            u, delta, A, B, C, D, z, delta_bias, dout, None, ctx.delta_softplus, False, hstates=hst, hdense=hd)
         dB = dB.to(B.dtype)
         dC = dC.to(C.dtype)
         dB = dB.squeeze(1) if ctx.squeeze_B else dB
@@ -161,8 +161,8 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         Bm = x_dblT[R8:R8 + d_state].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)                # (b,1,N,l) view
         Cm = x_dblT[R8 + d_state:].view(d_state, bsz, L).permute(1, 0, 2).unsqueeze(1)
         D = D.contiguous() if D is not None else None
-        _, _, out_z, hst = selective_scan_cuda.fwd_ex(conv1d_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus,
-                                                      direction=direction, want_out=False, want_x=False, want_hstates=True)
+        _, _, out_z, hst, hd = selective_scan_cuda.fwd_ex(conv1d_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, direction=direction,
+                                                          want_out=False, want_x=False, want_hstates=True, want_hdense=True)
         ctx.delta_softplus = delta_softplus
         ctx.direction = direction
         ctx.delta_rank = delta_rank
@@ -170,13 +170,13 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         # fit 16-32 GB parts.  With 180 GB of HBM the two (b, d_inner, l) tensors are kept instead (1.6 GB per training step
         # of the default model at batch 2), which removes one conv1d launch and one GEMM per direction from the backward.
         keep = (conv1d_out, delta) if KEEP_CONV_DELTA else (None, None)
-        ctx.save_for_backward(xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst, *keep)
+        ctx.save_for_backward(xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst, hd, *keep)
         return out_z
 
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, dout):
-        (xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst,
+        (xz, conv1d_weight, conv1d_bias, x_dblT, x_proj_weight, delta_proj_weight, A, D, delta_bias, hst, hd,
          conv1d_out, delta) = ctx.saved_tensors
         L = xz.shape[-1]
         delta_rank, R8 = ctx.delta_rank, delta_proj_weight.shape[1]     # the saved weights carry the zero padding (see forward)
@@ -197,7 +197,7 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         dx, dz = dxz.chunk(2, dim=1)
         dconv1d_out, ddelta, dA, dB, dC, dD, ddelta_bias, dz, _ = selective_scan_cuda.bwd_ex(
             conv1d_out, delta, A, Bm, Cm, D, z, delta_bias, dout, dz, ctx.delta_softplus, False,
-            direction=direction, hstates=hst)
+            direction=direction, hstates=hst, hdense=hd)
         dx_dblT = torch.empty_like(x_dblT)                                                                      # (R8+2N, b*l)
         dx_dblT[R8:R8 + d_state].view(d_state, bsz, L).copy_(dB.squeeze(1).permute(1, 0, 2))                    # :255-262
         dx_dblT[R8 + d_state:].view(d_state, bsz, L).copy_(dC.squeeze(1).permute(1, 0, 2))                      # :264-271

@@ -21,11 +21,12 @@ def _run_fwd_bwd(d, has_D=True, has_z=True, has_b=True, softplus=True, direction
     bias = d["delta_bias"] if has_b else None
     B = d["B"] if d["B"].dim() == 4 else d["B"].unsqueeze(1)
     C = d["C"] if d["C"].dim() == 4 else d["C"].unsqueeze(1)
-    out, x, out_z, hst = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, D, z, bias, softplus, direction=direction,
-                                    want_out=True, want_x=True, want_hstates=True)
-    # g: chunk-parallel recompute path (also returns the recomputed out_z); g2: the default state-stash sweep path
+    out, x, out_z, hst, hd = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, D, z, bias, softplus, direction=direction,
+                                        want_out=True, want_x=True, want_hstates=True, want_hdense=True)
+    # g: chunk-parallel path (also returns the recomputed out_z) -- with the saved states it is the scan-free main pass on the
+    # dense checkpoints, without them the recompute + warp-scan one; g2: the state-stash sweep path
     g = ssc.bwd_ex(d["u"], d["delta"], d["A"], B, C, D, z, bias, d["dout"], None, softplus, True, direction=direction,
-                   hstates=hst if use_hstates else None, low_memory=True)
+                   hstates=hst if use_hstates else None, hdense=hd if use_hstates else None, low_memory=True)
     g2 = ssc.bwd_ex(d["u"], d["delta"], d["A"], B, C, D, z, bias, d["dout"], None, softplus, False, direction=direction,
                     hstates=hst if use_hstates else None, low_memory=False)
     torch.cuda.synchronize()

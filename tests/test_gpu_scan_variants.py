@@ -19,9 +19,11 @@ VARIANTS = {
     "fwd_cp_async": {"SMB_FWD_V2": "1"},
     "fwd_single_buffered": {"SMB_FWD_V2": "0"},
     "ragg_v1": {"SMB_RAGG_V2": "0"},
-    "r3_v1": {"SMB_R3_V2": "0"},
+
     "seg256": {"SMB_SEG_MIN": "256"},
-    "legacy": {"SMB_FWD_V2": "0", "SMB_RAGG_V2": "0", "SMB_R3_V2": "0", "SMB_SEG_MIN": "256"},
+    "no_dense": {"DENSE": "0"},                      # 256-position checkpoints only: main backward pass with warp scans
+    "no_dense_r3_v1": {"DENSE": "0", "SMB_R3_V2": "0"},
+    "legacy": {"SMB_FWD_V2": "0", "SMB_RAGG_V2": "0", "SMB_R3_V2": "0", "SMB_SEG_MIN": "256", "DENSE": "0"},
 }
 ALL_SWITCHES = ("SMB_FWD_V2", "SMB_RAGG_V2", "SMB_R3_V2", "SMB_SEG_MIN")
 _oracle_cache = {}
@@ -42,10 +44,11 @@ def _run(d, direction, monkeypatch, env):
         else:
             monkeypatch.delenv(k, raising=False)
     B, C = d["B"].unsqueeze(1), d["C"].unsqueeze(1)
-    out, x, out_z, hst = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, direction=direction,
-                                    want_out=True, want_x=True, want_hstates=True)
+    monkeypatch.setattr(ssc, "DENSE_STATES", env.get("DENSE", "1") == "1")
+    out, x, out_z, hst, hd = ssc.fwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], True, direction=direction,
+                                        want_out=True, want_x=True, want_hstates=True, want_hdense=True)
     g = ssc.bwd_ex(d["u"], d["delta"], d["A"], B, C, d["D"], d["z"], d["delta_bias"], d["dout"], None, True, True,
-                   direction=direction, hstates=hst, low_memory=True)
+                   direction=direction, hstates=hst, hdense=hd, low_memory=True)
     torch.cuda.synchronize()
     return out, x, out_z, g
 

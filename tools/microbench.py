@@ -59,9 +59,11 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "microbench.json"))
     ap.add_argument("--stages", default="0,1,2,3")
     ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="A/B: 256-position checkpoints only (warp-scan main backward pass)")
     args = ap.parse_args()
     from segmamba_b200 import causal_conv1d_cuda as cc
     from segmamba_b200 import selective_scan_cuda as ssc
+    ssc.DENSE_STATES = not args.no_dense
     ref_ss, ref_cc = (None, None) if args.no_ref else (load_ref("selective_scan_cuda"), load_ref("causal_conv1d_cuda"))
     peaks = {}
     try:
@@ -95,11 +97,12 @@ def main():
                 bwd_bytes = s * batch * L * (7 * D + 2 * N) + 8 * batch * N * L + 4 * batch * (nck + 1) * N * D
                 conv_bytes = 2 * s * batch * D * L
                 r = {"dtype": dname, "batch": batch, "dim": D, "L": L}
-                hst = ssc.fwd_ex(u, delta, A, B, C, Dp, z, bias, True, want_out=False, want_x=False, want_hstates=True)[3]
+                _, _, _, hst, hd = ssc.fwd_ex(u, delta, A, B, C, Dp, z, bias, True, want_out=False, want_x=False, want_hstates=True,
+                                              want_hdense=True)
                 r["scan_fwd_ms"] = timeit(lambda: ssc.fwd_ex(u, delta, A, B, C, Dp, z, bias, True, want_out=False, want_x=False,
-                                                             want_hstates=True), args.iters, flush)
-                r["scan_bwd_ms"] = timeit(lambda: ssc.bwd_ex(u, delta, A, B, C, Dp, z, bias, dout, None, True, False, hstates=hst),
-                                          args.iters, flush)
+                                                             want_hstates=True, want_hdense=True), args.iters, flush)
+                r["scan_bwd_ms"] = timeit(lambda: ssc.bwd_ex(u, delta, A, B, C, Dp, z, bias, dout, None, True, False, hstates=hst,
+                                                             hdense=hd), args.iters, flush)
                 r["conv_fwd_ms"] = timeit(lambda: cc.causal_conv1d_fwd(u, w, cb, True), args.iters, flush)
                 r["conv_bwd_ms"] = timeit(lambda: cc.causal_conv1d_bwd(u, w, cb, dout, None, True), args.iters, flush)
                 ns = {262144: 64, 32768: 32, 4096: 16, 512: 8}.get(L, 8)
@@ -132,7 +135,7 @@ def main():
                     r["parity_conv_vs_refcuda"] = rel(cc.causal_conv1d_fwd(u, w, cb, True), ref_cc.causal_conv1d_fwd(u, w, cb, True))
                 rows.append(r)
                 print(json.dumps(r), flush=True)
-                del u, delta, z, dout, B, C, hst
+                del u, delta, z, dout, B, C, hst, hd
                 torch.cuda.empty_cache()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump({"hbm_peak_gbs": hbm, "rows": rows}, open(args.out, "w"), indent=1)

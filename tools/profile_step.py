@@ -63,8 +63,8 @@ def main():
         bias = torch.log(torch.expm1(0.001 + 0.1 * torch.rand(D, device=dev)))
 
         def run():
-            hst = ssc.fwd_ex(u, delta, A, B, C, Dp, z, bias, True, want_out=False, want_x=False, want_hstates=True)[3]
-            ssc.bwd_ex(u, delta, A, B, C, Dp, z, bias, dout, None, True, False, hstates=hst)
+            _, _, _, hst, hd = ssc.fwd_ex(u, delta, A, B, C, Dp, z, bias, True, want_out=False, want_x=False, want_hstates=True, want_hdense=True)
+            ssc.bwd_ex(u, delta, A, B, C, Dp, z, bias, dout, None, True, False, hstates=hst, hdense=hd)
         for _ in range(2):
             run()
         torch.cuda.synchronize()
