@@ -282,8 +282,8 @@ SMB_API int smb_layernorm_bwd(const smb_layernorm_bwd_args *args, void *cuda_str
  * out_dtype (SMB_F32 or the operand dtype).  epilogue: SMB_EPI_NONE, SMB_EPI_BIAS_N (+ bias[n], fp32),
  * SMB_EPI_BIAS_N_GELU (exact erf GELU after the bias, nn.GELU()), SMB_EPI_BIAS_M (+ bias[m]).
  * split_k > 1 (fp32 output only) partitions K over CTAs and ACCUMULATES into D with fp32 atomics; the caller
- * zero-initialises D (as with the reference's zero-initialised gradient accumulators).  accumulate != 0 does the
- * same with split_k == 1.
+ * zero-initialises D (as with the reference's zero-initialised gradient accumulators).  accumulate != 0 adds the
+ * product to the existing D (beta = 1: atomics for fp32, read-modify-write for 16-bit outputs).
  * ---------------------------------------------------------------------------------------------- */
 enum { SMB_MAJOR_K = 0, SMB_MAJOR_MN = 1 };
 enum { SMB_EPI_NONE = 0, SMB_EPI_BIAS_N = 1, SMB_EPI_BIAS_N_GELU = 2, SMB_EPI_BIAS_M = 3 };
@@ -295,7 +295,7 @@ typedef struct smb_gemm_args {
     int32_t a_major, b_major;   /* SMB_MAJOR_* */
     int32_t epilogue;           /* SMB_EPI_* */
     int32_t split_k;            /* >= 1 */
-    int32_t accumulate;         /* fp32 output: atomically add into D */
+    int32_t accumulate;         /* D += product instead of D = product */
     const void *A, *B;
     const float *bias;          /* may be NULL */
     void *D;

@@ -16,7 +16,7 @@ static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 #ifdef SMB_EMU
 // tcgen05 / tensor memory have no CPU emulation: the emulated library exports smb_gemm but every call fails loudly
-cudaError_t gemm_tc_launch(GemmP, const void *, int64_t, const void *, int64_t, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t gemm_tc_launch(GemmP, const void *, int64_t, const void *, int64_t, cudaStream_t, const char **) { return cudaErrorNotSupported; }
 int gemm_pick_bn(int) { return 0; }
 #endif
 }  // namespace smb
@@ -189,6 +189,10 @@ SMB_API int smb_scan_bwd(const smb_scan_bwd_args *a, void *cuda_stream) {
     p.stash = a->low_memory ? nullptr : reinterpret_cast<void *>(align_up(reinterpret_cast<size_t>(ws + 6 * ckf), 256));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     cudaError_t e;
+    {   // timing experiments (results are wrong when set): 1 = no dB/dC atomics, 2 = no cross-channel reduction, 4 = no state math
+        const char *dbg = getenv("SMB_R3_DBG");
+        p.dbg = dbg ? atoi(dbg) : 0;
+    }
     if (a->hdense && a->low_memory) {                     // scan-free main pass: no chunk states needed at all
         p.hd = const_cast<float *>(a->hdense);
         p.md = a->mdense;
@@ -388,8 +392,7 @@ SMB_API int smb_gemm(const smb_gemm_args *a, void *cuda_stream) {
         return fail(SMB_EINVAL, "smb_gemm: A and B must be 16-byte aligned");
     if (a->a_major < 0 || a->a_major > 1 || a->b_major < 0 || a->b_major > 1) return fail(SMB_EINVAL, "smb_gemm: bad operand major");
     if (a->epilogue < SMB_EPI_NONE || a->epilogue > SMB_EPI_BIAS_M) return fail(SMB_EINVAL, "smb_gemm: bad epilogue");
-    if ((a->split_k > 1 || a->accumulate) && a->out_dtype != SMB_F32)
-        return fail(SMB_EINVAL, "smb_gemm: split_k / accumulate need an fp32 output");
+    if (a->split_k > 1 && a->out_dtype != SMB_F32) return fail(SMB_EINVAL, "smb_gemm: split_k needs an fp32 output");
     if (a->ldd < a->N) return fail(SMB_EINVAL, "smb_gemm: ldd < N");
     // the contiguous extent of each operand as stored: K for a K-major operand, M / N for an MN-major one
     if (a->lda < (a->a_major == SMB_MAJOR_K ? a->K : a->M) || a->ldb < (a->b_major == SMB_MAJOR_K ? a->K : a->N))
@@ -401,8 +404,11 @@ SMB_API int smb_gemm(const smb_gemm_args *a, void *cuda_stream) {
     p.split_k = a->split_k < 1 ? 1 : a->split_k;
     p.atomic = (p.split_k > 1 || a->accumulate) ? 1 : 0;
     p.bias = a->bias; p.D = a->D; p.ldd = a->ldd;
-    cudaError_t e = smb::gemm_tc_launch(p, a->A, a->lda, a->B, a->ldb, (cudaStream_t)cuda_stream);
-    if (e != cudaSuccess) return cuda_fail(e, "smb_gemm");
+    const char *where = "";
+    cudaError_t e = smb::gemm_tc_launch(p, a->A, a->lda, a->B, a->ldb, (cudaStream_t)cuda_stream, &where);
+    if (e != cudaSuccess)
+        return fail(SMB_ECUDA, "smb_gemm: %s failed: CUDA error %d (%s) [M=%d N=%d K=%d a_major=%d b_major=%d lda=%lld ldb=%lld]", where,
+                    (int)e, cudaGetErrorString(e), a->M, a->N, a->K, a->a_major, a->b_major, (long long)a->lda, (long long)a->ldb);
     return SMB_OK;
 }
 

@@ -24,6 +24,7 @@ struct GemmP {
 };
 
 int gemm_pick_bn(int N);
-cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, int64_t ldb, cudaStream_t st);
+cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, int64_t ldb, cudaStream_t st,
+                           const char **where = nullptr);
 
 }  // namespace smb

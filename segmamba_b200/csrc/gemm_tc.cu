@@ -308,10 +308,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         for (int i = 0; i < kVec && c + i < n_valid; ++i) reinterpret_cast<float *>(dst)[i] = s[i];
                     }
                 } else {
-                    if (full_vec) {
+                    const TOut *s = reinterpret_cast<const TOut *>(src);
+                    if (p.atomic) {                      // D += result (no split-K for 16-bit outputs: plain read-modify-write)
+                        for (int i = 0; i < kVec && c + i < n_valid; ++i)
+                            dst[i] = static_cast<TOut>(static_cast<float>(dst[i]) + static_cast<float>(s[i]));
+                    } else if (full_vec) {
                         *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
                     } else {
-                        const TOut *s = reinterpret_cast<const TOut *>(src);
                         for (int i = 0; i < kVec && c + i < n_valid; ++i) dst[i] = s[i];
                     }
                 }
@@ -360,7 +363,10 @@ int gemm_pick_bn(int N) {
     return ((N + 15) / 16) * 16;
 }
 
-cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, int64_t ldb, cudaStream_t st) {
+cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, int64_t ldb, cudaStream_t st, const char **where) {
+    const char *dummy;
+    if (!where) where = &dummy;
+    *where = "setup";
     static int sms = 0, max_smem = 0;
     if (!sms) {
         int dev = 0;
@@ -386,14 +392,20 @@ cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, i
     p.tmem_cols = cols;
     if (p.split_k < 1) p.split_k = 1;
     if (p.split_k > kb_total) p.split_k = kb_total;
+    {   // no K slice may be empty: an accumulator that no MMA wrote would be added as is
+        const int kb_per = (kb_total + p.split_k - 1) / p.split_k;
+        p.split_k = (kb_total + kb_per - 1) / kb_per;
+    }
     const size_t smem = fixed + (size_t)stages * stage_bytes;
 
     CUtensorMap tmA, tmB;
     cudaError_t e;
+    *where = "tensor map of A (cuTensorMapEncodeTiled)";
     // A: K-major -> dims (K, M), box (64, 128); MN-major -> dims (M, K), box (64, 64) loaded twice per stage
     e = p.a_mn ? encode_2d(&tmA, A, p.dtype, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda * 2, 64, 64)
                : encode_2d(&tmA, A, p.dtype, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)lda * 2, 64, kBM);
     if (e != cudaSuccess) return e;
+    *where = "tensor map of B (cuTensorMapEncodeTiled)";
     e = p.b_mn ? encode_2d(&tmB, B, p.dtype, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)ldb * 2, 64, 64)
                : encode_2d(&tmB, B, p.dtype, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb * 2, 64, (uint32_t)BN);
     if (e != cudaSuccess) return e;
@@ -405,11 +417,13 @@ cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, i
 #define SMB_GEMM_LAUNCH(T)                                                                                                  \
     do {                                                                                                                    \
         static size_t set = 0;                                                                                              \
+        *where = "cudaFuncSetAttribute";                                                                                    \
         if (smem > set) {                                                                                                   \
             e = cudaFuncSetAttribute(gemm_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);        \
             if (e != cudaSuccess) return e;                                                                                 \
             set = (size_t)max_smem;                                                                                         \
         }                                                                                                                   \
+        *where = "kernel launch";                                                                                           \
         gemm_tc_kernel<T><<<grid, kThreads, smem, st>>>(tmA, tmB, p);                                                       \
     } while (0)
     if (p.out_dtype == 0) SMB_GEMM_LAUNCH(float);

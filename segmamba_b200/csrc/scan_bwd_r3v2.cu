@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         const float A2a = __shfl_sync(0xffffffffu, A2_l, n), A2b = __shfl_sync(0xffffffffu, A2_l, n + 1);
         const float hia = __shfl_sync(0xffffffffu, hin_l, n), hib = __shfl_sync(0xffffffffu, hin_l, n + 1);
         const float mia = __shfl_sync(0xffffffffu, min_l, n), mib = __shfl_sync(0xffffffffu, min_l, n + 1);
-        if (active) {
+        if (active && !(p.dbg & 4)) {
             if constexpr (kDense) {
                 const float2 hv = use_h ? *reinterpret_cast<const float2 *>(hdp + n) : f2(0.f, 0.f);
                 const float2 mv = use_m ? *reinterpret_cast<const float2 *>(mdp + n) : f2(0.f, 0.f);
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         rowB += 2 * kPad; rowC += 2 * kPad;
         __syncthreads();
         // ---- reduce dB / dC of the two states over the CTA's channels: 16-byte vectors, fixed trip count ----
-        if (rpos0 < L) {
+        if (rpos0 < L && !(p.dbg & 2)) {
             float4 v[kW];
 #pragma unroll
             for (int w2 = 0; w2 < kW; ++w2) v[w2] = *reinterpret_cast<const float4 *>(rsrc + w2 * kPad);
@@ -381,7 +381,9 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
                                                     __fadd2_rn(f2(v[2].z, v[2].w), f2(v[3].z, v[3].w))),
                                          __fadd2_rn(__fadd2_rn(f2(v[4].z, v[4].w), f2(v[5].z, v[5].w)),
                                                     __fadd2_rn(f2(v[6].z, v[6].w), f2(v[7].z, v[7].w))));
-            if (vec_ok && rpos0 + 3 < L) {
+            if (p.dbg & 1) {
+                if (lo.x == 1.2345e33f) rdst[0] = hi.y;      // keep the sums live
+            } else if (vec_ok && rpos0 + 3 < L) {
                 if (!rev) red_add_v4(rdst + rpos0, lo.x, lo.y, hi.x, hi.y);
                 else red_add_v4(rdst + (L - 4 - rpos0), hi.y, hi.x, lo.y, lo.x);
             } else {

@@ -41,6 +41,7 @@ struct ScanP {
     // dense checkpoints (every 8th scan position), see dense_slot(): hd = forward state entering a block (written by the
     // forward main pass, read by R3), md = local adjoint entering a block from the right (written by R1, read by R3)
     float *hd, *md;
+    int dbg;                                       // timing experiments only (SMB_R3_DBG, results are wrong when set): see scan_bwd_r3v2.cu
 };
 
 // Dense checkpoint layout, chosen for the reader: R3's CTA = (256-position chunk, channel octet) finds its 32 blocks x 8

@@ -128,6 +128,10 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None, None
 
 
+def _is_mn(t: torch.Tensor) -> bool:
+    return t.stride(0) == 1 and t.stride(1) != 1
+
+
 class _MatmulNT(torch.autograd.Function):
     """D = a @ b.T for 2-D operands of either major (a: (M, K), b: (N, K)), 16-bit arithmetic operands, fp32 accumulation.
     Gradients on the same kernel: da = dD @ b (B operand = b.T view), db = dD.T @ a (both operands transposed views)."""
@@ -152,19 +156,28 @@ class _MatmulNT(torch.autograd.Function):
         da = db = None
         M, N = dD.shape
         K = aq.shape[1]
-        if ctx.needs_input_grad[0]:          # (M, N) x (K, N)^T, contraction over N
+        # each gradient is produced in the storage layout of its operand (an MN-major operand gets the transposed product),
+        # so no transpose copy follows: e.g. out_proj's activation gradient comes out channel-major, as the scans want it
+        if ctx.needs_input_grad[0]:          # da = dD @ b: contraction over N
             big = N >= 16384 and M * K <= 1 << 21
-            da = gemm(dD, bq.t(), out_dtype=torch.float32 if big else None, split_k=_split_k_for(N) if big else 1).to(ctx.a_dtype)
-        if ctx.needs_input_grad[1]:          # (N, M) x (K, M)^T, contraction over M
+            kw = dict(out_dtype=torch.float32 if big else None, split_k=_split_k_for(N) if big else 1)
+            da = gemm(bq.t(), dD, **kw).t() if _is_mn(aq) else gemm(dD, bq.t(), **kw)
+            da = da.to(ctx.a_dtype)
+        if ctx.needs_input_grad[1]:          # db = dD.T @ a: contraction over M
             big = M >= 16384 and N * K <= 1 << 21
-            db = gemm(dD.t(), aq.t(), out_dtype=torch.float32 if big else None, split_k=_split_k_for(M) if big else 1).to(ctx.b_dtype)
+            kw = dict(out_dtype=torch.float32 if big else None, split_k=_split_k_for(M) if big else 1)
+            db = gemm(aq.t(), dD.t(), **kw).t() if _is_mn(bq) else gemm(dD.t(), aq.t(), **kw)
+            db = db.to(ctx.b_dtype)
         return da, db, None, None
 
 
 def matmul_nt(a: torch.Tensor, b: torch.Tensor, compute_dtype: torch.dtype | None = None, out_dtype: torch.dtype | None = None):
     """a @ b.T on the native GEMM (differentiable).  a: (M, K), b: (N, K); each needs one contiguous axis."""
     if compute_dtype is None:
-        compute_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else a.dtype
+        if torch.is_autocast_enabled("cuda"):
+            compute_dtype = torch.get_autocast_dtype("cuda")
+        else:
+            compute_dtype = a.dtype if a.dtype in (torch.float16, torch.bfloat16) else b.dtype
     if compute_dtype not in (torch.float16, torch.bfloat16):
         raise RuntimeError("gemm.matmul_nt: 16-bit operands only (fp32 inputs need autocast or compute_dtype)")
     return _MatmulNT.apply(a, b, compute_dtype, out_dtype)

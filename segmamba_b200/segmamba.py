@@ -20,11 +20,27 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import gemm as _gemm
 from . import layer_norm
 from .instance_norm import fused_instance_norm
 from .mamba_simple import Mamba
 
 _CL = torch.channels_last_3d
+
+def _pointwise(conv: nn.Conv3d, x: torch.Tensor, gelu: bool = False) -> torch.Tensor:
+    """1x1x1 convolution (+ exact GELU) of a channels-last activation.  With 16-bit arithmetic (autocast) it is one
+    (tokens, C_in) x (C_out, C_in)^T product on the native tensor-core GEMM, bias and GELU applied in the accumulator epilogue;
+    in fp32 (no autocast) it stays the library convolution the reference calls (segmamba.py:81-89,103-107)."""
+    cd = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    if (x.is_cuda and cd in (torch.float16, torch.bfloat16) and conv.kernel_size == (1, 1, 1) and conv.stride == (1, 1, 1)
+            and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0
+            and x.is_contiguous(memory_format=_CL) and (x.numel() // conv.in_channels) % 8 == 0):
+        if gelu and conv.bias is None:
+            return F.gelu(_gemm.conv1x1(x, conv.weight, None))
+        return _gemm.conv1x1(x, conv.weight, conv.bias, gelu=gelu)
+    y = conv(x)
+    return F.gelu(y) if gelu else y
+
 
 class _Conv(nn.Sequential):
     """stand-in for monai Convolution(conv_only-like: act=None, norm=None): a Sequential with one child `conv`."""
@@ -59,7 +75,7 @@ class UnetResBlock(nn.Module):
         out = fused_instance_norm(self.conv1.conv(inp), "leaky_relu", 0.01)   # dynunet_block.py:100-102
         out = self.conv2(out)
         if self.downsample:                                                               # :105-110
-            return fused_instance_norm(out, "leaky_relu", 0.01, add=self.conv3.conv(inp), add_norm=True)
+            return fused_instance_norm(out, "leaky_relu", 0.01, add=_pointwise(self.conv3.conv, inp), add_norm=True)
         return fused_instance_norm(out, "leaky_relu", 0.01, add=inp)
 
 
@@ -143,7 +159,7 @@ class MlpChannel(nn.Module):
         self.fc2 = nn.Conv3d(mlp_dim, hidden_size, 1)
 
     def forward(self, x):
-        return self.fc2(self.act(self.fc1(x)))
+        return _pointwise(self.fc2, _pointwise(self.fc1, x, gelu=True))      # act = exact-erf nn.GELU(), fused into fc1's epilogue
 
 
 class GSC(nn.Module):
@@ -168,8 +184,8 @@ class GSC(nn.Module):
         x_residual = x
         x1 = fused_instance_norm(self.proj(x), "relu")
         x1 = fused_instance_norm(self.proj2(x1), "relu")
-        x2 = fused_instance_norm(self.proj3(x), "relu")
-        x = fused_instance_norm(self.proj4(x1 + x2), "relu")
+        x2 = fused_instance_norm(_pointwise(self.proj3, x), "relu")
+        x = fused_instance_norm(_pointwise(self.proj4, x1 + x2), "relu")
         return x + x_residual
 
 
