@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--bf16-params", action="store_true",
                     help="bf16 matmul / convolution parameters with fp32 masters in the optimizer (segmamba_b200/master_weights.py): "
                          "same arithmetic as autocast, two multi-tensor copies per step instead of ~400 cast kernels")
+    ap.add_argument("--amp", default="bf16", choices=["bf16", "fp16"],
+                    help="autocast dtype of the step: bf16 (BASELINE.json) or fp16 + GradScaler, which is what the reference's trainer runs "
+                         "(light_training/trainer.py:67,450,461-466)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="edge of the cubic crop the CPU arm runs per step")
     ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of the CPU arm (0: min(cores this process may use, 32))")
     ap.add_argument("--workload", default="train_step", choices=["train_step", "sliding_window"],
@@ -199,8 +202,9 @@ def main_reference(args):
 
 
 def workload_name(args):
+    amp = "bf16 autocast" if getattr(args, "amp", "bf16") == "bf16" else "fp16 autocast + GradScaler (the reference trainer's setting)"
     return (f"SegMamba default (depths [2,2,2,2], dims [48,96,192,384]) training step on synthetic 4x{args.patch}^3 patches, "
-            f"batch {args.batch}/GPU, bf16 autocast, CE loss, SGD nesterov + clip (BASELINE.json configs[2])")
+            f"batch {args.batch}/GPU, {amp}, CE loss, SGD nesterov + clip (BASELINE.json configs[2])")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -370,13 +374,27 @@ def main_native(args):
     loss_host = torch.zeros(1).pin_memory()
     mf = torch.channels_last_3d if args.channels_last else torch.contiguous_format
 
+    amp_dtype = torch.float16 if args.amp == "fp16" else torch.bfloat16
+    scaler = torch.amp.GradScaler() if args.amp == "fp16" else None                                        # trainer.py:67
+
     def step(x, y):
         opt.zero_grad(set_to_none=True)
         if mw is not None:
             mw.zero_grad()
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast("cuda", dtype=amp_dtype):
             logits = net(x.contiguous(memory_format=mf))
             loss = torch.nn.functional.cross_entropy(logits.float(), y)
+        if scaler is not None:                                                                             # trainer.py:461-466
+            scaler.scale(loss).backward()
+            if mw is not None:
+                mw.grads_to_master()
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(opt_params, 12.0)
+            scaler.step(opt)
+            scaler.update()
+            if mw is not None:
+                mw.master_to_model()
+            return loss
         loss.backward()
         if mw is not None:
             mw.grads_to_master()
@@ -529,7 +547,7 @@ def main_native(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.amp,
             "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2: one step touches > 10 GB of activations (126 MB L2)",

@@ -353,6 +353,7 @@ cudaError_t encode_2d(CUtensorMap *m, const void *base, int dtype, uint64_t inne
     const CUresult r = fn(m, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
                           dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) return cudaErrorDeviceUninitialized;
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
@@ -400,6 +401,15 @@ cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, i
 
     CUtensorMap tmA, tmB;
     cudaError_t e;
+    {   // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context in the calling thread.  PyTorch's autograd worker
+        // threads select their device lazily, so a backward whose first CUDA work is this GEMM arrives here with no context
+        // bound (seen on hardware as CUDA_ERROR_INVALID_CONTEXT).  Bind the primary context of the device that owns A.
+        *where = "cudaPointerGetAttributes(A)";
+        cudaPointerAttributes attr;
+        if ((e = cudaPointerGetAttributes(&attr, A)) != cudaSuccess) return e;
+        if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) return cudaErrorInvalidDevicePointer;
+        if ((e = cudaSetDevice(attr.device)) != cudaSuccess) return e;
+    }
     *where = "tensor map of A (cuTensorMapEncodeTiled)";
     // A: K-major -> dims (K, M), box (64, 128); MN-major -> dims (M, K), box (64, 64) loaded twice per stage
     e = p.a_mn ? encode_2d(&tmA, A, p.dtype, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)lda * 2, 64, 64)

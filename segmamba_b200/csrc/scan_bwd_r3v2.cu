@@ -317,6 +317,8 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         mdp = p.md + slot;
         use_h = active && jl < L;                       // blocks past the end were never written
         use_m = use_h && lane < 31 && jl + kRun < L;    // the chunk's / sequence's last block starts from Min alone
+        if (use_h) prefetch_l2(hdp);                    // N * 4 = 64 bytes each: in L2 by the time the state loop wants them
+        if (use_m) prefetch_l2(mdp);
     }
     float2 dt2[kRun / 2], dtu2[kRun / 2], g2[kRun / 2], sLB2[kRun / 2], sAq2[kRun / 2], yy2[kRun / 2];
     float sumdt = 0.f;
@@ -349,6 +351,12 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
     __syncthreads();   // B/C tiles and the zero rows are ready
 
     const float *rowB = sB + bo, *rowC = sC + bo;
+    // dense checkpoints of the state pair one round ahead (a global load issued a round early, consumed after ~2 x 100 instructions)
+    float2 hv_nx = f2(0.f, 0.f), mv_nx = f2(0.f, 0.f);
+    if (kDense) {
+        if (use_h) hv_nx = *reinterpret_cast<const float2 *>(hdp);
+        if (use_m) mv_nx = *reinterpret_cast<const float2 *>(mdp);
+    }
 #pragma unroll 1
     for (int n = 0; n < N; n += 2) {
         const float A2a = __shfl_sync(0xffffffffu, A2_l, n), A2b = __shfl_sync(0xffffffffu, A2_l, n + 1);
@@ -356,8 +364,11 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         const float mia = __shfl_sync(0xffffffffu, min_l, n), mib = __shfl_sync(0xffffffffu, min_l, n + 1);
         if (active && !(p.dbg & 4)) {
             if constexpr (kDense) {
-                const float2 hv = use_h ? *reinterpret_cast<const float2 *>(hdp + n) : f2(0.f, 0.f);
-                const float2 mv = use_m ? *reinterpret_cast<const float2 *>(mdp + n) : f2(0.f, 0.f);
+                const float2 hv = hv_nx, mv = mv_nx;
+                if (n + 2 < N) {
+                    if (use_h) hv_nx = *reinterpret_cast<const float2 *>(hdp + n + 2);
+                    if (use_m) mv_nx = *reinterpret_cast<const float2 *>(mdp + n + 2);
+                }
                 const float ma = fmaf(ex2(A2a * suffix), mia, mv.x), mb = fmaf(ex2(A2b * suffix), mib, mv.y);
                 r3_state<true>(rowB, rowC, A2a, hv.x, ma, sumdt, lane, dt2, dtu2, g2, sLB2, sAq2, yy2, myB0, myC0, sda + n);
                 r3_state<true>(rowB + kPad, rowC + kPad, A2b, hv.y, mb, sumdt, lane, dt2, dtu2, g2, sLB2, sAq2, yy2, myB1, myC1, sda + n + 1);

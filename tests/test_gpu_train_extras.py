@@ -65,3 +65,30 @@ def test_master_weights_step_matches_autocast_step():
     for k, v in ref_model.state_dict().items():
         assert sd[k].dtype == v.dtype
         assert_close(sd[k], v, 2e-2, k)
+
+
+def test_fp16_gradscaler_step_matches_bf16_step():
+    """the reference trainer's actual setting: fp16 autocast + GradScaler (light_training/trainer.py:67,450,461-466).  Three
+    TrainStep iterations stay finite, take real optimiser steps (no skipped step after the first scale adjustment window), and
+    track the bf16 step's losses."""
+    import copy
+    import golden_inputs as gi
+    from segmamba_b200.segmamba import SegMamba
+    from segmamba_b200.train_step import TrainStep
+    c = gi.MODEL_CASE
+    torch.manual_seed(9)
+    m16 = SegMamba(in_chans=4, out_chans=4, depths=c["depths"], feat_size=c["feat_size"], hidden_size=c["hidden_size"]).cuda()
+    mbf = copy.deepcopy(m16)
+    mk = lambda m: torch.optim.SGD(m.parameters(), lr=1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    s16 = TrainStep(m16, mk(m16), torch.nn.CrossEntropyLoss(), autocast_dtype=torch.float16)
+    sbf = TrainStep(mbf, mk(mbf), torch.nn.CrossEntropyLoss(), autocast_dtype=torch.bfloat16)
+    assert s16.grad_scaler is not None
+    g = torch.Generator().manual_seed(2)
+    w0 = m16.out.conv.conv.weight.detach().clone()
+    for i in range(3):
+        x = torch.rand(2, 4, 32, 32, 32, generator=g).cuda()
+        y = torch.randint(0, 4, (2, 32, 32, 32), generator=g).cuda()
+        la, lb = float(s16(x, y)), float(sbf(x, y))
+        assert la == la and abs(la - lb) <= 3e-2 * abs(lb), (i, la, lb)
+    assert all(torch.isfinite(p).all() for p in m16.parameters())
+    assert not torch.equal(w0, m16.out.conv.conv.weight.detach())            # the scaler did not skip every step
