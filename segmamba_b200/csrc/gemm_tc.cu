@@ -108,6 +108,22 @@ __device__ __forceinline__ void tc_ld16(unsigned taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4f(float *a, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start >> 4 at [0,14), leading byte offset >> 4
 // at [16,30), stride byte offset >> 4 at [32,46), version 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64)).
 //   K-major  tile = rows x 128 B : 8-row groups are 1024 B apart (SBO); the leading offset is unused inside one swizzle row.
@@ -136,6 +152,17 @@ template <> __device__ __forceinline__ unsigned pack2<__half>(float a, float b) 
     return *reinterpret_cast<unsigned *>(&h);
 }
 
+// packed 16-bit pair `old` + (a, b), rounded once
+template <typename T> __device__ __forceinline__ unsigned add2(unsigned old, float a, float b);
+template <> __device__ __forceinline__ unsigned add2<__nv_bfloat16>(unsigned old, float a, float b) {
+    const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162 *>(&old);
+    return pack2<__nv_bfloat16>(__low2float(o) + a, __high2float(o) + b);
+}
+template <> __device__ __forceinline__ unsigned add2<__half>(unsigned old, float a, float b) {
+    const __half2 o = *reinterpret_cast<const __half2 *>(&old);
+    return pack2<__half>(__low2float(o) + a, __high2float(o) + b);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // TOut: __nv_bfloat16 / __half (store) or float (store, or atomic accumulate when p.atomic)
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -152,9 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int b_tile = p.b_mn ? ((BN + 63) / 64) * 8192 : BN * 128;
     const int stage_bytes = a_tile + ((b_tile + 1023) & ~1023);
     uint8_t *stage0 = smem;
-    uint8_t *staging = smem + (size_t)p.stages * stage_bytes;
-    const int pitch = BN * (int)sizeof(TOut) + 16;      // staging row pitch: 16 bytes off a multiple of 128 -> conflict-free rows
-    uint64_t *bars = reinterpret_cast<uint64_t *>(staging + (((size_t)kBM * pitch + 15) & ~(size_t)15));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
     uint64_t *full = bars, *empty = bars + kMaxStages, *tfull = bars + 2 * kMaxStages, *tempty = bars + 2 * kMaxStages + 2;
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + 2 * kMaxStages + 4);
     (void)b_rows;
@@ -242,10 +267,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
     } else {
         // ------------------------------- epilogue warps (2..5): TMEM lane quadrant = warp % 4 -------------------------------
+        // Each thread owns one accumulator row (its TMEM lane) and writes it straight from registers: 32 columns per tcgen05.ld,
+        // i.e. 64 (16-bit) or 128 (fp32) contiguous bytes of the row per step -- whole 32-byte sectors, no staging tile and no
+        // CTA-level barrier.  The next 32 columns are loaded while the current ones are converted and stored.
         const int q = warp & 3;
         const int row = q * 32 + lane;                   // row of the tile this thread drains
-        const int et = threadIdx.x - 64;                 // 0..127 among the epilogue threads
         unsigned tc = 0;
+        TOut *const D = reinterpret_cast<TOut *>(p.D);
         for (int t = blockIdx.x; t < n_work; t += gridDim.x, ++tc) {
             const int nb = (t / p.split_k) % n_tiles, mb = t / (p.split_k * n_tiles);
             const int sp = t % p.split_k;
@@ -253,73 +281,90 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             mbar_wait(&tfull[as], (tc >> 1) & 1);
             tc_fence_after();
             const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * BN);
-            uint8_t *srow = staging + (size_t)row * pitch;
             const int n0 = nb * BN;
-            const float bias_m = (p.epilogue == GEMM_EPI_BIAS_M && p.bias && mb * kBM + row < p.M && (sp == 0)) ? p.bias[mb * kBM + row] : 0.f;
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float v[16];
-                tc_ld16(taddr + (unsigned)c0, v);
-                if (p.epilogue == GEMM_EPI_BIAS_N || p.epilogue == GEMM_EPI_BIAS_N_GELU) {
+            const int m = mb * kBM + row;
+            const int n_valid = min(BN, p.N - n0);
+            const bool warp_has_rows = mb * kBM + q * 32 < p.M;      // whole-warp condition: tcgen05.ld is .sync.aligned
+            const bool row_ok = m < p.M;
+            const float bias_m = (p.epilogue == GEMM_EPI_BIAS_M && p.bias && row_ok && sp == 0) ? p.bias[m] : 0.f;
+            TOut *drow = D + (int64_t)m * p.ldd + n0;
+            const bool vec_ok = (reinterpret_cast<uintptr_t>(drow) & 15) == 0;
+            if (warp_has_rows) {
+                unsigned cur[32];
+                tc_ld32(taddr, cur);
+                for (int c0 = 0; c0 < n_valid; c0 += 32) {
+                    tc_wait_ld();
+                    const bool more = c0 + 32 < n_valid;
+                    float v[32];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int n = n0 + c0 + i;
-                        v[i] += (p.bias && n < p.N && sp == 0) ? __ldg(p.bias + n) : 0.f;
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cur[i]);
+                    // the next 32 columns load into `cur` while `v` is converted and stored (v is live across the load, so the two
+                    // sets never share registers; `cur` is not read again before the wait at the top of the loop)
+                    if (more) tc_ld32(taddr + (unsigned)(c0 + 32), cur);
+                    if (p.epilogue == GEMM_EPI_BIAS_N || p.epilogue == GEMM_EPI_BIAS_N_GELU) {
+                        if (p.bias && sp == 0) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] += (n0 + c0 + i < p.N) ? __ldg(p.bias + n0 + c0 + i) : 0.f;
+                        }
+                        if (p.epilogue == GEMM_EPI_BIAS_N_GELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                        }
+                    } else if (p.epilogue == GEMM_EPI_BIAS_M) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += bias_m;
                     }
-                    if (p.epilogue == GEMM_EPI_BIAS_N_GELU) {
+                    if (row_ok) {
+                        const int cols = min(32, n_valid - c0);
+                        if constexpr (sizeof(TOut) == 4) {
+                            float *dst = reinterpret_cast<float *>(drow) + c0;
+                            if (vec_ok && cols == 32) {
+                                if (p.atomic) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+                                    for (int i = 0; i < 8; ++i) red_add_v4f(dst + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) *reinterpret_cast<F4 *>(dst + 4 * i) = F4{v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
+                                }
+                            } else {
+                                for (int i = 0; i < cols; ++i) {
+                                    if (p.atomic) atomicAdd(dst + i, v[i]);
+                                    else dst[i] = v[i];
+                                }
+                            }
+                        } else {
+                            TOut *dst = drow + c0;
+                            if (vec_ok && cols == 32) {
+                                uint4 pk[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    pk[i] = make_uint4(pack2<TOut>(v[8 * i], v[8 * i + 1]), pack2<TOut>(v[8 * i + 2], v[8 * i + 3]),
+                                                       pack2<TOut>(v[8 * i + 4], v[8 * i + 5]), pack2<TOut>(v[8 * i + 6], v[8 * i + 7]));
+                                if (p.atomic) {                   // D += product (16-bit outputs: plain read-modify-write, no split-K)
+                                    uint4 old[4];
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) old[i] = *reinterpret_cast<const uint4 *>(dst + 8 * i);
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        pk[i] = make_uint4(add2<TOut>(old[i].x, v[8 * i], v[8 * i + 1]), add2<TOut>(old[i].y, v[8 * i + 2], v[8 * i + 3]),
+                                                           add2<TOut>(old[i].z, v[8 * i + 4], v[8 * i + 5]), add2<TOut>(old[i].w, v[8 * i + 6], v[8 * i + 7]));
+                                    }
+                                }
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4 *>(dst + 8 * i) = pk[i];
+                            } else {
+                                for (int i = 0; i < cols; ++i) {
+                                    const float o = p.atomic ? static_cast<float>(dst[i]) + v[i] : v[i];
+                                    dst[i] = static_cast<TOut>(o);
+                                }
+                            }
+                        }
                     }
-                } else if (p.epilogue == GEMM_EPI_BIAS_M) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += bias_m;
-                }
-                if constexpr (sizeof(TOut) == 4) {
-                    F4 *dst = reinterpret_cast<F4 *>(srow + c0 * 4);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = F4{v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
-                } else {
-                    uint4 *dst = reinterpret_cast<uint4 *>(srow + c0 * 2);
-                    dst[0] = make_uint4(pack2<TOut>(v[0], v[1]), pack2<TOut>(v[2], v[3]), pack2<TOut>(v[4], v[5]), pack2<TOut>(v[6], v[7]));
-                    dst[1] = make_uint4(pack2<TOut>(v[8], v[9]), pack2<TOut>(v[10], v[11]), pack2<TOut>(v[12], v[13]), pack2<TOut>(v[14], v[15]));
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);      // accumulator buffer drained: the MMA warp may reuse it
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // ---- staging tile -> global, coalesced: consecutive threads take consecutive 16-byte pieces of a row ----
-            constexpr int kVec = 16 / (int)sizeof(TOut);
-            const int n_valid = min(BN, p.N - n0);
-            const int pieces = (n_valid + kVec - 1) / kVec;
-            const int m_valid = min(kBM, p.M - mb * kBM);
-            TOut *D = reinterpret_cast<TOut *>(p.D);
-            for (int idx = et; idx < m_valid * pieces; idx += kEpiThreads) {
-                const int r = idx / pieces, c = (idx - r * pieces) * kVec;
-                const uint8_t *src = staging + (size_t)r * pitch + (size_t)c * sizeof(TOut);
-                TOut *dst = D + (int64_t)(mb * kBM + r) * p.ldd + n0 + c;
-                const bool full_vec = (c + kVec <= n_valid) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-                if constexpr (sizeof(TOut) == 4) {
-                    const float *s = reinterpret_cast<const float *>(src);
-                    if (p.atomic) {
-                        for (int i = 0; i < kVec && c + i < n_valid; ++i) atomicAdd(reinterpret_cast<float *>(dst) + i, s[i]);
-                    } else if (full_vec) {
-                        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
-                    } else {
-                        for (int i = 0; i < kVec && c + i < n_valid; ++i) reinterpret_cast<float *>(dst)[i] = s[i];
-                    }
-                } else {
-                    const TOut *s = reinterpret_cast<const TOut *>(src);
-                    if (p.atomic) {                      // D += result (no split-K for 16-bit outputs: plain read-modify-write)
-                        for (int i = 0; i < kVec && c + i < n_valid; ++i)
-                            dst[i] = static_cast<TOut>(static_cast<float>(dst[i]) + static_cast<float>(s[i]));
-                    } else if (full_vec) {
-                        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
-                    } else {
-                        for (int i = 0; i < kVec && c + i < n_valid; ++i) dst[i] = s[i];
-                    }
-                }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");    // staging tile free for the next tile
         }
     }
     tc_fence_before();
@@ -376,20 +421,17 @@ cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, i
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
     if (p.BN <= 0) p.BN = gemm_pick_bn(p.N);
-    if (p.out_dtype == 0 && p.BN > 128) p.BN = 128;      // fp32 staging tile: 128 x (BN * 4 + 16) bytes must leave room for >= 2 stages
     const int BN = p.BN;
-    const size_t osz = p.out_dtype == 0 ? 4 : 2;
     const size_t b_tile = p.b_mn ? (size_t)((BN + 63) / 64) * 8192 : (size_t)BN * 128;
     const size_t stage_bytes = (size_t)kBM * 128 + ((b_tile + 1023) & ~(size_t)1023);
-    const size_t staging = (((size_t)kBM * (BN * osz + 16)) + 15) & ~(size_t)15;
-    const size_t fixed = 1024 + staging + (2 * kMaxStages + 4) * 8 + 16;
+    const size_t fixed = 1024 + (2 * kMaxStages + 4) * 8 + 16;
     int stages = (int)(((size_t)max_smem - fixed) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     const int kb_total = (p.K + kBK - 1) / kBK;
     if (stages < 2) return cudaErrorInvalidConfiguration;
     p.stages = stages;
     int cols = 32;
-    while (cols < 2 * BN) cols <<= 1;
+    while (cols < 2 * BN + ((BN & 31) ? 16 : 0)) cols <<= 1;   // the epilogue reads 32 columns at a time: keep its last read inside the allocation
     p.tmem_cols = cols;
     if (p.split_k < 1) p.split_k = 1;
     if (p.split_k > kb_total) p.split_k = kb_total;

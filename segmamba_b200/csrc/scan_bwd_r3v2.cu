@@ -223,12 +223,13 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x, b = blockIdx.z;
+    // blockIdx.y = (B/C group, run of p.opc consecutive channel octets of that group): the CTA stages the chunk's B / C tile once
+    // and walks its octets one after the other, prefetching the next octet's operands into L2 while it works on the current one
     const int octs_per_group = (p.dim_per_group + kW - 1) / kW;
-    const int g = blockIdx.y / octs_per_group;
-    const int d0 = g * p.dim_per_group + (blockIdx.y - g * octs_per_group) * kW;
-    const int nch = min(kW, (g + 1) * p.dim_per_group - d0);
-    const int d = d0 + warp;
-    const bool active = warp < nch;
+    const int runs_per_group = (octs_per_group + p.opc - 1) / p.opc;
+    const int g = blockIdx.y / runs_per_group;
+    const int oct_begin = (blockIdx.y - g * runs_per_group) * p.opc;
+    const int oct_end = min(octs_per_group, oct_begin + p.opc);
     const int jc = chunk * kCkpt;
     const int jl = jc + lane * kRun;
     const bool rev = p.reverse;
@@ -255,6 +256,43 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
             sC[n * kPad + so] = to_f32<T>(vc[n]);
         }
     }
+
+    const int bo = padp(lane * kRun);                   // this lane's run inside a padded row
+    float *myB0 = slab + (0 * kW + warp) * kPad + bo;   // state 0 of the round: dB row, dC row
+    float *myC0 = slab + (1 * kW + warp) * kPad + bo;
+    float *myB1 = slab + (2 * kW + warp) * kPad + bo;   // state 1 of the round
+    float *myC1 = slab + (3 * kW + warp) * kPad + bo;
+    float *sda = sDA + (warp * 32 + lane) * kDaPitch;
+    // reduction role of this thread: (state of the round, tensor) x 4 consecutive positions
+    const int combo = threadIdx.x >> 6, pg = threadIdx.x & 63;
+    const int rpos0 = jc + 4 * pg;
+    const float *rsrc = slab + (size_t)combo * kW * kPad + padp(4 * pg);
+    float *const rdst0 = ((combo & 1) ? p.dC : p.dB) + (((int64_t)b * p.G + g) * N + (combo >> 1)) * (int64_t)L;
+    const bool vec_ok = (L & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.dB) | reinterpret_cast<uintptr_t>(p.dC)) & 15) == 0;
+
+    // L2 prefetch of one octet's operand runs (16 bytes per lane and tensor) and dense checkpoints
+    auto prefetch_octet = [&](int oct) {
+        const int dd0 = g * p.dim_per_group + oct * kW;
+        const int dd = dd0 + warp;
+        if (dd >= (g + 1) * p.dim_per_group || jl >= L) return;
+        const int tok = rev ? max(L - 1 - jl - 7, 0) : jl;
+        prefetch_l2(reinterpret_cast<const T *>(p.u) + b * p.u_bs + (int64_t)dd * p.u_ds + tok);
+        prefetch_l2(reinterpret_cast<const T *>(p.delta) + b * p.delta_bs + (int64_t)dd * p.delta_ds + tok);
+        prefetch_l2(reinterpret_cast<const T *>(p.dout) + b * p.dout_bs + (int64_t)dd * p.dout_ds + tok);
+        if (kHasZ) prefetch_l2(reinterpret_cast<const T *>(p.z) + b * p.z_bs + (int64_t)dd * p.z_ds + tok);
+        if (kDense) {
+            const int64_t slot = dense_slot(p, b, g, dd, chunk * 32 + lane, N);
+            prefetch_l2(p.hd + slot);
+            if (lane < 31) prefetch_l2(p.md + slot);
+        }
+    };
+
+#pragma unroll 1
+    for (int oct = oct_begin; oct < oct_end; ++oct) {
+    const int d0 = g * p.dim_per_group + oct * kW;
+    const int nch = min(kW, (g + 1) * p.dim_per_group - d0);
+    const int d = d0 + warp;
+    const bool active = warp < nch;
 
     // ---- per-lane runs ----
     float dt[kRun], uu[kRun], gg[kRun];
@@ -285,14 +323,9 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
 #pragma unroll
         for (int i = 0; i < kRun; ++i) { dt[i] = 0.f; uu[i] = 0.f; gg[i] = 0.f; }
     }
+    if (oct + 1 < oct_end) prefetch_octet(oct + 1);
 
-    const int bo = padp(lane * kRun);                   // this lane's run inside a padded row
-    float *myB0 = slab + (0 * kW + warp) * kPad + bo;   // state 0 of the round: dB row, dC row
-    float *myC0 = slab + (1 * kW + warp) * kPad + bo;
-    float *myB1 = slab + (2 * kW + warp) * kPad + bo;   // state 1 of the round
-    float *myC1 = slab + (3 * kW + warp) * kPad + bo;
-    float *sda = sDA + (warp * 32 + lane) * kDaPitch;
-    if (!active) {                                      // rows of absent channels stay zero for the whole kernel
+    if (!active) {                                      // rows of absent channels stay zero for the whole octet
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4 *>(myB0) = z4; *reinterpret_cast<float4 *>(myB0 + 4) = z4;
         *reinterpret_cast<float4 *>(myC0) = z4; *reinterpret_cast<float4 *>(myC0 + 4) = z4;
@@ -317,8 +350,6 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         mdp = p.md + slot;
         use_h = active && jl < L;                       // blocks past the end were never written
         use_m = use_h && lane < 31 && jl + kRun < L;    // the chunk's / sequence's last block starts from Min alone
-        if (use_h) prefetch_l2(hdp);                    // N * 4 = 64 bytes each: in L2 by the time the state loop wants them
-        if (use_m) prefetch_l2(mdp);
     }
     float2 dt2[kRun / 2], dtu2[kRun / 2], g2[kRun / 2], sLB2[kRun / 2], sAq2[kRun / 2], yy2[kRun / 2];
     float sumdt = 0.f;
@@ -342,13 +373,8 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         suffix = inc - sumdt;
     }
 
-    // reduction role of this thread: (state of the round, tensor) x 4 consecutive positions
-    const int combo = threadIdx.x >> 6, pg = threadIdx.x & 63;
-    const int rpos0 = jc + 4 * pg;
-    const float *rsrc = slab + (size_t)combo * kW * kPad + padp(4 * pg);
-    float *rdst = ((combo & 1) ? p.dC : p.dB) + (((int64_t)b * p.G + g) * N + (combo >> 1)) * (int64_t)L;
-    const bool vec_ok = (L & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.dB) | reinterpret_cast<uintptr_t>(p.dC)) & 15) == 0;
-    __syncthreads();   // B/C tiles and the zero rows are ready
+    float *rdst = rdst0;
+    __syncthreads();   // B/C tiles (first octet) and the zero rows are ready; the previous octet's reductions are done
 
     const float *rowB = sB + bo, *rowC = sC + bo;
     // dense checkpoints of the state pair one round ahead (a global load issued a round early, consumed after ~2 x 100 instructions)
@@ -408,7 +434,7 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         __syncthreads();
     }
 
-    if (!active) return;
+    if (active) {
     // ---- dA: column sums of this warp's (lane, state) partials ----
     __syncwarp();
     if (lane < N) {
@@ -421,6 +447,7 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         }
         atomicAdd(p.dA + (int64_t)d * N + lane, (s0 + s1) + (s2 + s3));
     }
+    __syncwarp();                                        // the next octet's partials overwrite these rows
     float sLB[kRun], sAq[kRun], yy[kRun];
 #pragma unroll
     for (int j = 0; j < kRun / 2; ++j) {
@@ -473,20 +500,34 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
         if (p.dD) atomicAdd(p.dD + d, dDacc);
         if (p.ddelta_bias) atomicAdd(p.ddelta_bias + d, dbacc);
     }
+    }   // active
+    }   // octets
 }
 
 template <typename T, int N, bool kHasZ>
 cudaError_t launch_main2(const ScanP &p, cudaStream_t st) {
     const size_t sm = R3Smem<N>::kBytes;
     cudaError_t e;
-    const int octs = ((p.dim_per_group + kW - 1) / kW) * p.G;
-    dim3 grid(p.nck, octs, p.batch);
+    // octets per CTA: as many as keeps >= ~4 CTAs per resident slot (2 x 148) in the grid
+    const int opg = (p.dim_per_group + kW - 1) / kW;
+    ScanP q = p;
+    {
+        const long total = (long)p.nck * opg * p.G * p.batch;
+        long opc = total / 1184;
+        if (opc < 1) opc = 1;
+        if (opc > opg) opc = opg;
+        const char *e = getenv("SMB_R3_OPC");            // A/B switch: octets per CTA (1 = one CTA per octet, as in round 1)
+        if (e && atoi(e) > 0) opc = atoi(e) > opg ? opg : atoi(e);
+        q.opc = (int)opc;
+    }
+    const int runs = ((opg + q.opc - 1) / q.opc) * p.G;
+    dim3 grid(p.nck, runs, p.batch);
     if (p.hd && p.md) {
         SMB_SET_SMEM_ONCE((scan_bwd_main2_kernel<T, N, kHasZ, true>), sm);
-        scan_bwd_main2_kernel<T, N, kHasZ, true><<<grid, kW * 32, sm, st>>>(p); count_launch();
+        scan_bwd_main2_kernel<T, N, kHasZ, true><<<grid, kW * 32, sm, st>>>(q); count_launch();
     } else {
         SMB_SET_SMEM_ONCE((scan_bwd_main2_kernel<T, N, kHasZ, false>), sm);
-        scan_bwd_main2_kernel<T, N, kHasZ, false><<<grid, kW * 32, sm, st>>>(p); count_launch();
+        scan_bwd_main2_kernel<T, N, kHasZ, false><<<grid, kW * 32, sm, st>>>(q); count_launch();
     }
     return cudaGetLastError();
 }

@@ -41,6 +41,7 @@ struct ScanP {
     // dense checkpoints (every 8th scan position), see dense_slot(): hd = forward state entering a block (written by the
     // forward main pass, read by R3), md = local adjoint entering a block from the right (written by R1, read by R3)
     float *hd, *md;
+    int opc;                                       // R3: channel octets handled by one CTA (scan_bwd_r3v2.cu)
     int dbg;                                       // timing experiments only (SMB_R3_DBG, results are wrong when set): see scan_bwd_r3v2.cu
 };
 

@@ -21,11 +21,13 @@ VARIANTS = {
     "ragg_v1": {"SMB_RAGG_V2": "0"},
 
     "seg256": {"SMB_SEG_MIN": "256"},
+    "r3_opc1": {"SMB_R3_OPC": "1"},                   # one CTA per channel octet (no octet walk)
+    "r3_opc3": {"SMB_R3_OPC": "3"},                   # three octets per CTA whatever the problem size
     "no_dense": {"DENSE": "0"},                      # 256-position checkpoints only: main backward pass with warp scans
     "no_dense_r3_v1": {"DENSE": "0", "SMB_R3_V2": "0"},
     "legacy": {"SMB_FWD_V2": "0", "SMB_RAGG_V2": "0", "SMB_R3_V2": "0", "SMB_SEG_MIN": "256", "DENSE": "0"},
 }
-ALL_SWITCHES = ("SMB_FWD_V2", "SMB_RAGG_V2", "SMB_R3_V2", "SMB_SEG_MIN")
+ALL_SWITCHES = ("SMB_FWD_V2", "SMB_RAGG_V2", "SMB_R3_V2", "SMB_SEG_MIN", "SMB_R3_OPC")
 _oracle_cache = {}
 
 
