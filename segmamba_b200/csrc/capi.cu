@@ -404,6 +404,10 @@ SMB_API int smb_gemm(const smb_gemm_args *a, void *cuda_stream) {
     p.split_k = a->split_k < 1 ? 1 : a->split_k;
     p.atomic = (p.split_k > 1 || a->accumulate) ? 1 : 0;
     p.bias = a->bias; p.D = a->D; p.ldd = a->ldd;
+    {   // measurement aid: SMB_GEMM_PROF = device address (decimal) of 8 uint64 counters that receive the per-role wait cycles
+        const char *pe = getenv("SMB_GEMM_PROF");
+        p.prof = pe ? reinterpret_cast<unsigned long long *>(strtoull(pe, nullptr, 10)) : nullptr;
+    }
     const char *where = "";
     cudaError_t e = smb::gemm_tc_launch(p, a->A, a->lda, a->B, a->ldb, (cudaStream_t)cuda_stream, &where);
     if (e != cudaSuccess)

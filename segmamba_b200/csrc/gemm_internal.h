@@ -21,6 +21,7 @@ struct GemmP {
     const float *bias;
     void *D;
     int64_t ldd;            // elements
+    unsigned long long *prof;   // optional 8 device counters: cycles in barrier waits per role (gemm_tc.cu), else nullptr
 };
 
 int gemm_pick_bn(int N);

@@ -9,7 +9,7 @@
 // backward products (data gradient: the same kernel on the transposed weight view; weight gradient: contraction over the token
 // axis, both operands MN-major, split over CTAs along K with fp32 atomics).
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes of A (128 x 64) and B (BN x 64) per 64-wide K block into a
 //               ring of shared-memory stages (CU_TENSOR_MAP_SWIZZLE_128B), completion on the stage's `full` mbarrier
 //   warp 1      allocates tensor memory; one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BN, K = 16)
@@ -40,8 +40,8 @@ namespace {
 constexpr int kBM = 128;            // UMMA M (one CTA, cta_group::1): accumulator row i lives in tensor-memory lane i
 constexpr int kBK = 64;             // K block: 64 sixteen-bit elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 6;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -73,6 +73,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
         if (done) return;
         if (spins > (1u << 24)) __trap();
     }
+}
+// optional profiling (GemmP::prof != nullptr): cycles a role spends inside a barrier wait, summed over the grid
+__device__ __forceinline__ void mbar_wait_prof(uint64_t *bar, unsigned parity, unsigned long long *acc) {
+    if (!acc) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    atomicAdd(acc, (unsigned long long)(clock64() - t0));
 }
 __device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *m, int c0, int c1, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -163,6 +170,16 @@ template <> __device__ __forceinline__ unsigned add2<__half>(unsigned old, float
     return pack2<__half>(__low2float(o) + a, __high2float(o) + b);
 }
 
+template <typename T> __device__ __forceinline__ unsigned sum2(unsigned a, unsigned b);
+template <> __device__ __forceinline__ unsigned sum2<__nv_bfloat16>(unsigned a, unsigned b) {
+    const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162 *>(&a), y = *reinterpret_cast<const __nv_bfloat162 *>(&b);
+    return pack2<__nv_bfloat16>(__low2float(x) + __low2float(y), __high2float(x) + __high2float(y));
+}
+template <> __device__ __forceinline__ unsigned sum2<__half>(unsigned a, unsigned b) {
+    const __half2 x = *reinterpret_cast<const __half2 *>(&a), y = *reinterpret_cast<const __half2 *>(&b);
+    return pack2<__half>(__low2float(x) + __low2float(y), __high2float(x) + __high2float(y));
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // TOut: __nv_bfloat16 / __half (store) or float (store, or atomic accumulate when p.atomic)
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -179,14 +196,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int b_tile = p.b_mn ? ((BN + 63) / 64) * 8192 : BN * 128;
     const int stage_bytes = a_tile + ((b_tile + 1023) & ~1023);
     uint8_t *stage0 = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
+    uint8_t *staging = smem + (size_t)p.stages * stage_bytes;                 // 8 warps x 32 rows x 144 bytes
+    uint64_t *bars = reinterpret_cast<uint64_t *>(staging + kEpiWarps * 32 * 144);
     uint64_t *full = bars, *empty = bars + kMaxStages, *tfull = bars + 2 * kMaxStages, *tempty = bars + 2 * kMaxStages + 2;
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + 2 * kMaxStages + 4);
     (void)b_rows;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -200,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const unsigned tmem_base = *tmem_slot;
+    const long long t_start = clock64();
 
     const int m_tiles = (p.M + kBM - 1) / kBM;
     const int n_tiles = (p.N + BN - 1) / BN;
@@ -216,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % p.stages;
                     const unsigned ph = (it / p.stages) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_wait_prof(&empty[s], ph ^ 1, p.prof ? p.prof + 0 : nullptr);
                     uint8_t *sa = stage0 + (size_t)s * stage_bytes, *sb = sa + a_tile;
                     mbar_expect_tx(&full[s], (unsigned)(a_tile + b_tile));
                     if (!p.a_mn) {
@@ -245,12 +264,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 const int sp = t % p.split_k;
                 const int kb0 = sp * kb_per, kb1 = min(kb_total, kb0 + kb_per);
                 const int as = tc & 1;
-                mbar_wait(&tempty[as], ((tc >> 1) & 1) ^ 1);
+                mbar_wait_prof(&tempty[as], ((tc >> 1) & 1) ^ 1, p.prof ? p.prof + 1 : nullptr);
                 tc_fence_after();
                 const unsigned d_tmem = tmem_base + (unsigned)(as * BN);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % p.stages;
-                    mbar_wait(&full[s], (it / p.stages) & 1);
+                    mbar_wait_prof(&full[s], (it / p.stages) & 1, p.prof ? p.prof + 2 : nullptr);
                     tc_fence_after();
                     const unsigned sa = smem_u32(stage0 + (size_t)s * stage_bytes), sb = sa + a_tile;
                     const int k_left = p.K - kb * kBK;
@@ -267,99 +286,123 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
     } else {
         // ------------------------------- epilogue warps (2..5): TMEM lane quadrant = warp % 4 -------------------------------
-        // Each thread owns one accumulator row (its TMEM lane) and writes it straight from registers: 32 columns per tcgen05.ld,
-        // i.e. 64 (16-bit) or 128 (fp32) contiguous bytes of the row per step -- whole 32-byte sectors, no staging tile and no
-        // CTA-level barrier.  The next 32 columns are loaded while the current ones are converted and stored.
-        const int q = warp & 3;
-        const int row = q * 32 + lane;                   // row of the tile this thread drains
+        // A thread drains one accumulator row (its TMEM lane), 32 columns per tcgen05.ld with the next load in flight, and parks
+        // the converted values in a warp-private staging tile of 32 rows x 128 bytes; the warp then writes the tile out with 8
+        // lanes per row, i.e. one full 128-byte line per row and four lines per store instruction.  (Storing each thread's own row
+        // straight from registers costs one LSU transaction per 16 bytes: measured 3.2 us per 128 x 256 tile, four times the
+        // HBM time of the tile.)  No CTA-level barrier: the tile is private to the warp.
+        const int q = warp & 3;                          // TMEM lanes 32 q .. 32 q + 31 (a warp may only touch its own quadrant)
+        const int half = (warp - 2) >> 2;                // two warps share a quadrant: each drains half of the column groups
         unsigned tc = 0;
         TOut *const D = reinterpret_cast<TOut *>(p.D);
+        constexpr int kPitch = 144;                      // staging row pitch: 128 + 16 bytes -> conflict-free 16-byte accesses
+        constexpr int kGC = 128 / (int)sizeof(TOut);     // columns per staged group: 64 (16-bit) or 32 (fp32)
+        constexpr int kVec = 16 / (int)sizeof(TOut);
+        uint8_t *stg = staging + (size_t)(warp - 2) * (32 * kPitch);
         for (int t = blockIdx.x; t < n_work; t += gridDim.x, ++tc) {
             const int nb = (t / p.split_k) % n_tiles, mb = t / (p.split_k * n_tiles);
             const int sp = t % p.split_k;
             const int as = tc & 1;
-            mbar_wait(&tfull[as], (tc >> 1) & 1);
+            mbar_wait_prof(&tfull[as], (tc >> 1) & 1, (p.prof && lane == 0 && half == 0) ? p.prof + 3 + q : nullptr);
             tc_fence_after();
             const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * BN);
             const int n0 = nb * BN;
-            const int m = mb * kBM + row;
+            const int m0 = mb * kBM + q * 32;             // first row of this warp
             const int n_valid = min(BN, p.N - n0);
-            const bool warp_has_rows = mb * kBM + q * 32 < p.M;      // whole-warp condition: tcgen05.ld is .sync.aligned
-            const bool row_ok = m < p.M;
-            const float bias_m = (p.epilogue == GEMM_EPI_BIAS_M && p.bias && row_ok && sp == 0) ? p.bias[m] : 0.f;
-            TOut *drow = D + (int64_t)m * p.ldd + n0;
-            const bool vec_ok = (reinterpret_cast<uintptr_t>(drow) & 15) == 0;
-            if (warp_has_rows) {
+            const float bias_m = (p.epilogue == GEMM_EPI_BIAS_M && p.bias && m0 + lane < p.M && sp == 0) ? p.bias[m0 + lane] : 0.f;
+            // column groups of this warp: [g_begin, g_end), the first / second half of the tile's groups
+            const int n_groups = (n_valid + kGC - 1) / kGC;
+            const int g_begin = half ? ((n_groups + 1) / 2) * kGC : 0;
+            const int g_end = half ? n_valid : min(n_valid, ((n_groups + 1) / 2) * kGC);
+            if (m0 < p.M && g_begin < g_end) {            // whole-warp condition: tcgen05.ld is .sync.aligned
                 unsigned cur[32];
-                tc_ld32(taddr, cur);
-                for (int c0 = 0; c0 < n_valid; c0 += 32) {
-                    tc_wait_ld();
-                    const bool more = c0 + 32 < n_valid;
-                    float v[32];
+                tc_ld32(taddr + (unsigned)g_begin, cur);
+                for (int g0 = g_begin; g0 < g_end; g0 += kGC) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cur[i]);
-                    // the next 32 columns load into `cur` while `v` is converted and stored (v is live across the load, so the two
-                    // sets never share registers; `cur` is not read again before the wait at the top of the loop)
-                    if (more) tc_ld32(taddr + (unsigned)(c0 + 32), cur);
-                    if (p.epilogue == GEMM_EPI_BIAS_N || p.epilogue == GEMM_EPI_BIAS_N_GELU) {
-                        if (p.bias && sp == 0) {
+                    for (int h = 0; h < kGC / 32; ++h) {
+                        const int c0 = g0 + 32 * h;
+                        if (c0 < g_end) {
+                            tc_wait_ld();
+                            float v[32];
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] += (n0 + c0 + i < p.N) ? __ldg(p.bias + n0 + c0 + i) : 0.f;
-                        }
-                        if (p.epilogue == GEMM_EPI_BIAS_N_GELU) {
+                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cur[i]);
+                            // the next 32 columns load into `cur` while `v` is converted and staged (v is live across the load, so
+                            // the two never share registers; `cur` is not read again before the next wait)
+                            if (c0 + 32 < g_end) tc_ld32(taddr + (unsigned)(c0 + 32), cur);
+                            if (p.epilogue == GEMM_EPI_BIAS_N || p.epilogue == GEMM_EPI_BIAS_N_GELU) {
+                                if (p.bias && sp == 0) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                        }
-                    } else if (p.epilogue == GEMM_EPI_BIAS_M) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += bias_m;
-                    }
-                    if (row_ok) {
-                        const int cols = min(32, n_valid - c0);
-                        if constexpr (sizeof(TOut) == 4) {
-                            float *dst = reinterpret_cast<float *>(drow) + c0;
-                            if (vec_ok && cols == 32) {
-                                if (p.atomic) {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) red_add_v4f(dst + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                                } else {
-#pragma unroll
-                                    for (int i = 0; i < 8; ++i) *reinterpret_cast<F4 *>(dst + 4 * i) = F4{v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
+                                    for (int i = 0; i < 32; ++i) v[i] += (n0 + c0 + i < p.N) ? __ldg(p.bias + n0 + c0 + i) : 0.f;
                                 }
-                            } else {
-                                for (int i = 0; i < cols; ++i) {
-                                    if (p.atomic) atomicAdd(dst + i, v[i]);
-                                    else dst[i] = v[i];
+                                if (p.epilogue == GEMM_EPI_BIAS_N_GELU) {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
                                 }
+                            } else if (p.epilogue == GEMM_EPI_BIAS_M) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] += bias_m;
                             }
-                        } else {
-                            TOut *dst = drow + c0;
-                            if (vec_ok && cols == 32) {
-                                uint4 pk[4];
+                            uint8_t *srow = stg + lane * kPitch + h * 64;
+                            if constexpr (sizeof(TOut) == 4) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) *reinterpret_cast<F4 *>(srow + 16 * i) = F4{v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
+                            } else {
 #pragma unroll
                                 for (int i = 0; i < 4; ++i)
-                                    pk[i] = make_uint4(pack2<TOut>(v[8 * i], v[8 * i + 1]), pack2<TOut>(v[8 * i + 2], v[8 * i + 3]),
-                                                       pack2<TOut>(v[8 * i + 4], v[8 * i + 5]), pack2<TOut>(v[8 * i + 6], v[8 * i + 7]));
-                                if (p.atomic) {                   // D += product (16-bit outputs: plain read-modify-write, no split-K)
-                                    uint4 old[4];
+                                    *reinterpret_cast<uint4 *>(srow + 16 * i) =
+                                        make_uint4(pack2<TOut>(v[8 * i], v[8 * i + 1]), pack2<TOut>(v[8 * i + 2], v[8 * i + 3]),
+                                                   pack2<TOut>(v[8 * i + 4], v[8 * i + 5]), pack2<TOut>(v[8 * i + 6], v[8 * i + 7]));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // ---- write the group out: lane -> (row = 4 it + lane / 8, 16-byte piece = lane % 8) ----
 #pragma unroll
-                                    for (int i = 0; i < 4; ++i) old[i] = *reinterpret_cast<const uint4 *>(dst + 8 * i);
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = 4 * it + (lane >> 3), pc = lane & 7;
+                        const int col = g0 + pc * kVec, m = m0 + r;
+                        if (m < p.M && col < n_valid) {
+                            const uint8_t *src = stg + r * kPitch + pc * 16;
+                            TOut *dst = D + (int64_t)m * p.ldd + n0 + col;
+                            const bool full = (col + kVec <= n_valid) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+                            if constexpr (sizeof(TOut) == 4) {
+                                const F4 sv = *reinterpret_cast<const F4 *>(src);
+                                float *fd = reinterpret_cast<float *>(dst);
+                                if (full) {
+                                    if (p.atomic) red_add_v4f(fd, sv.x, sv.y, sv.z, sv.w);
+                                    else *reinterpret_cast<F4 *>(fd) = sv;
+                                } else {
+                                    const float e4[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
                                     for (int i = 0; i < 4; ++i) {
-                                        pk[i] = make_uint4(add2<TOut>(old[i].x, v[8 * i], v[8 * i + 1]), add2<TOut>(old[i].y, v[8 * i + 2], v[8 * i + 3]),
-                                                           add2<TOut>(old[i].z, v[8 * i + 4], v[8 * i + 5]), add2<TOut>(old[i].w, v[8 * i + 6], v[8 * i + 7]));
+                                        if (col + i < n_valid) {
+                                            if (p.atomic) atomicAdd(fd + i, e4[i]);
+                                            else fd[i] = e4[i];
+                                        }
                                     }
                                 }
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4 *>(dst + 8 * i) = pk[i];
                             } else {
-                                for (int i = 0; i < cols; ++i) {
-                                    const float o = p.atomic ? static_cast<float>(dst[i]) + v[i] : v[i];
-                                    dst[i] = static_cast<TOut>(o);
+                                uint4 sv = *reinterpret_cast<const uint4 *>(src);
+                                if (full) {
+                                    if (p.atomic) {                   // D += product (16-bit outputs: read-modify-write, no split-K)
+                                        const uint4 o = *reinterpret_cast<const uint4 *>(dst);
+                                        sv = make_uint4(sum2<TOut>(o.x, sv.x), sum2<TOut>(o.y, sv.y), sum2<TOut>(o.z, sv.z), sum2<TOut>(o.w, sv.w));
+                                    }
+                                    *reinterpret_cast<uint4 *>(dst) = sv;
+                                } else {
+                                    const TOut *se = reinterpret_cast<const TOut *>(&sv);
+#pragma unroll
+                                    for (int i = 0; i < kVec; ++i) {
+                                        if (col + i < n_valid) {
+                                            const float o = p.atomic ? static_cast<float>(dst[i]) + static_cast<float>(se[i]) : static_cast<float>(se[i]);
+                                            dst[i] = static_cast<TOut>(o);
+                                        }
+                                    }
                                 }
                             }
                         }
                     }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -369,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (p.prof && threadIdx.x == 0) atomicAdd(p.prof + 7, (unsigned long long)(clock64() - t_start));
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -424,7 +468,7 @@ cudaError_t gemm_tc_launch(GemmP p, const void *A, int64_t lda, const void *B, i
     const int BN = p.BN;
     const size_t b_tile = p.b_mn ? (size_t)((BN + 63) / 64) * 8192 : (size_t)BN * 128;
     const size_t stage_bytes = (size_t)kBM * 128 + ((b_tile + 1023) & ~(size_t)1023);
-    const size_t fixed = 1024 + (2 * kMaxStages + 4) * 8 + 16;
+    const size_t fixed = 1024 + kEpiWarps * 32 * 144 + (2 * kMaxStages + 4) * 8 + 16;
     int stages = (int)(((size_t)max_smem - fixed) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     const int kb_total = (p.K + kBK - 1) / kBK;

@@ -11,6 +11,7 @@ GSC.proj3 / proj4 (segmamba.py:103-107) and UnetResBlock.conv3 (dynunet_block.py
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 from torch.amp import custom_bwd, custom_fwd
@@ -18,6 +19,15 @@ from torch.amp import custom_bwd, custom_fwd
 from . import _lib
 
 EPI_NONE, EPI_BIAS_N, EPI_BIAS_N_GELU, EPI_BIAS_M = 0, 1, 2, 3
+
+# Which products of the model run on the native kernel (measured per shape against the library on B200, profiles/r2j_gemm_bench.md):
+#   "auto" (default)  the products that contract over the token axis -- every weight gradient of the mixer (dW of in_proj /
+#                     x_proj / dt_proj / out_proj; K = 65 536 ... 524 288 tokens split over the SMs with fp32 atomics): native
+#                     1.07 - 1.40 x the library; the activation-sized products (output = tokens x channels), where the kernel
+#                     reaches 0.4 - 0.8 x the library, stay library calls, as in the reference;
+#   "all"             every pointwise contraction and 1x1x1 convolution;      "off"  none.
+MODE = os.environ.get("SMB_GEMM", "auto")
+SPLIT_TOKENS = 16384     # contraction length from which the split-K path is used (and wins)
 
 
 def _operand(t: torch.Tensor, what: str):
@@ -96,7 +106,12 @@ class _Linear(torch.autograd.Function):
         epi = EPI_NONE if bias is None else (EPI_BIAS_N_GELU if gelu else EPI_BIAS_N)
         if gelu and bias is None:
             raise RuntimeError("linear: gelu epilogue needs a bias (pass zeros)")
-        y = gemm(xq, wq, bias, epi)                           # bias (+ exact GELU) applied in the accumulator epilogue
+        if MODE == "all":
+            y = gemm(xq, wq, bias, epi)                       # bias (+ exact GELU) applied in the accumulator epilogue
+        else:
+            y = torch.nn.functional.linear(xq, wq, bias.to(cd) if bias is not None else None)
+            if gelu:
+                y = torch.nn.functional.gelu(y)
         ctx.save_for_backward(xq, wq, bias if gelu else None)   # the pre-activation is recomputed in the backward
         ctx.gelu, ctx.has_bias = gelu, bias is not None
         ctx.x_dtype, ctx.w_dtype, ctx.w_shape = x.dtype, weight.dtype, weight.shape
@@ -113,15 +128,20 @@ class _Linear(torch.autograd.Function):
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         if ctx.gelu:
-            p32 = gemm(xq, wq, bias, EPI_BIAS_N, out_dtype=torch.float32)
+            p32 = (gemm(xq, wq, bias, EPI_BIAS_N, out_dtype=torch.float32) if MODE == "all"
+                   else torch.nn.functional.linear(xq, wq, bias.to(xq.dtype)).float())
             cdf = 0.5 * (1 + torch.erf(p32 * 0.7071067811865476))
             pdf = torch.exp(-0.5 * p32 * p32) * 0.3989422804014327
             dy2 = (dy2.float() * (cdf + p32 * pdf)).to(xq.dtype)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(dy2, wq.t()).reshape(*dy.shape[:-1], wq.shape[1]).to(ctx.x_dtype)        # (tokens, N) x (C_in, N)^T
+            dx = (gemm(dy2, wq.t()) if MODE == "all" else dy2 @ wq)                            # (tokens, N) x (C_in, N)^T
+            dx = dx.reshape(*dy.shape[:-1], wq.shape[1]).to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
-            dw = gemm(dy2.t(), xq.t(), out_dtype=torch.float32, split_k=_split_k_for(dy2.shape[0]))   # (N, tokens) x (C_in, tokens)^T
+            if MODE == "all" or (MODE == "auto" and dy2.shape[0] >= SPLIT_TOKENS and supported(dy2.t(), xq.t())):
+                dw = gemm(dy2.t(), xq.t(), out_dtype=torch.float32, split_k=_split_k_for(dy2.shape[0]))   # (N, tokens) x (C_in, tokens)^T
+            else:
+                dw = dy2.t() @ xq
             dw = dw.reshape(ctx.w_shape).to(ctx.w_dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy2.float().sum(0).to(ctx.b_dtype)
@@ -143,6 +163,8 @@ class _MatmulNT(torch.autograd.Function):
         bq = b if b.dtype == compute_dtype else b.to(compute_dtype)
         ctx.save_for_backward(aq, bq)
         ctx.a_dtype, ctx.b_dtype = a.dtype, b.dtype
+        if MODE != "all":
+            return (aq @ bq.t()).to(out_dtype or compute_dtype)
         return gemm(aq, bq, out_dtype=out_dtype or compute_dtype)
 
     @staticmethod
@@ -158,15 +180,18 @@ class _MatmulNT(torch.autograd.Function):
         K = aq.shape[1]
         # each gradient is produced in the storage layout of its operand (an MN-major operand gets the transposed product),
         # so no transpose copy follows: e.g. out_proj's activation gradient comes out channel-major, as the scans want it
+        def prod(x, y, big, contraction):
+            """x @ y.T; native when the routing says so (see MODE)"""
+            if MODE == "all" or (MODE == "auto" and big and supported(x, y)):
+                return gemm(x, y, out_dtype=torch.float32 if big else None, split_k=_split_k_for(contraction) if big else 1)
+            return x @ y.t()
         if ctx.needs_input_grad[0]:          # da = dD @ b: contraction over N
-            big = N >= 16384 and M * K <= 1 << 21
-            kw = dict(out_dtype=torch.float32 if big else None, split_k=_split_k_for(N) if big else 1)
-            da = gemm(bq.t(), dD, **kw).t() if _is_mn(aq) else gemm(dD, bq.t(), **kw)
+            big = N >= SPLIT_TOKENS and M * K <= 1 << 21
+            da = prod(bq.t(), dD, big, N).t() if _is_mn(aq) else prod(dD, bq.t(), big, N)
             da = da.to(ctx.a_dtype)
         if ctx.needs_input_grad[1]:          # db = dD.T @ a: contraction over M
-            big = M >= 16384 and N * K <= 1 << 21
-            kw = dict(out_dtype=torch.float32 if big else None, split_k=_split_k_for(M) if big else 1)
-            db = gemm(aq.t(), dD.t(), **kw).t() if _is_mn(bq) else gemm(dD.t(), aq.t(), **kw)
+            big = M >= SPLIT_TOKENS and N * K <= 1 << 21
+            db = prod(aq.t(), dD.t(), big, M).t() if _is_mn(bq) else prod(dD.t(), aq.t(), big, M)
             db = db.to(ctx.b_dtype)
         return da, db, None, None
 

@@ -24,7 +24,7 @@ from .selective_scan_interface import mamba_inner_fn_no_out_proj
 def _tc_ok(x2d, weight):
     """the native GEMM takes 16-bit operands: autocast on, or 16-bit activations; rows must be 16-byte multiples"""
     cd = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x2d.dtype
-    return (x2d.is_cuda and cd in (torch.float16, torch.bfloat16) and x2d.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0
+    return (_gemm.MODE != "off" and x2d.is_cuda and cd in (torch.float16, torch.bfloat16) and x2d.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0
             and x2d.shape[0] % 8 == 0)
 
 

@@ -32,7 +32,7 @@ def _pointwise(conv: nn.Conv3d, x: torch.Tensor, gelu: bool = False) -> torch.Te
     (tokens, C_in) x (C_out, C_in)^T product on the native tensor-core GEMM, bias and GELU applied in the accumulator epilogue;
     in fp32 (no autocast) it stays the library convolution the reference calls (segmamba.py:81-89,103-107)."""
     cd = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
-    if (x.is_cuda and cd in (torch.float16, torch.bfloat16) and conv.kernel_size == (1, 1, 1) and conv.stride == (1, 1, 1)
+    if (_gemm.MODE == "all" and x.is_cuda and cd in (torch.float16, torch.bfloat16) and conv.kernel_size == (1, 1, 1) and conv.stride == (1, 1, 1)
             and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0
             and x.is_contiguous(memory_format=_CL) and (x.numel() // conv.in_channels) % 8 == 0):
         if gelu and conv.bias is None:

@@ -116,8 +116,9 @@ def _mm_nt(a, b, out=None, accumulate=False, out_dtype=None, split_tokens=0):
     """a @ b.T for 2-D views.  16-bit operands run on the native tensor-core GEMM (smb_gemm; no operand is copied: a view whose
     first axis is contiguous goes in MN-major); fp32 operands (the module used without autocast) stay a library call.
     split_tokens: length of the contraction when it runs over the token axis (weight gradients) -> split-K with fp32 atomics."""
-    if a.dtype in (torch.float16, torch.bfloat16) and a.is_cuda and _gemm.supported(a, b):
-        sk = _gemm._split_k_for(split_tokens) if split_tokens >= 16384 else 1
+    native = _gemm.MODE == "all" or (_gemm.MODE == "auto" and split_tokens >= _gemm.SPLIT_TOKENS)
+    if native and a.dtype in (torch.float16, torch.bfloat16) and a.is_cuda and _gemm.supported(a, b):
+        sk = _gemm._split_k_for(split_tokens) if split_tokens >= _gemm.SPLIT_TOKENS else 1
         od = torch.float32 if sk > 1 else out_dtype
         return _gemm.gemm(a, b, out=out, accumulate=accumulate, out_dtype=od, split_k=sk)   # split-K results stay fp32
     res = a @ b.t()
@@ -223,7 +224,8 @@ class MambaInnerFnNoOutProj(torch.autograd.Function):
         ntok = bsz * L
         ddelta2 = _as_dbl(ddelta)                                                                               # :272
         ddelta_proj_weight = _mm_nt(ddelta2, x_dblT[:R8], split_tokens=ntok)                                    # :273
-        _mm_nt(delta_proj_weight.t(), ddelta2.t(), out=dx_dblT[:R8])   # rows delta_rank..R8 come out as exact zeros  :274
+        # (R8, d) copy of the small weight: as a transposed VIEW its rows would be 16 bytes long, a TMA box shape that crawls
+        _mm_nt(delta_proj_weight.t().contiguous(), ddelta2.t(), out=dx_dblT[:R8])   # rows delta_rank..R8 are exact zeros  :274
         dconv2 = _as_dbl(dconv1d_out)                                                                           # :275
         dx_proj_weight = _mm_nt(dx_dblT, conv2, split_tokens=ntok)                                              # :276
         dconv2 = _mm_nt(x_proj_weight.t(), dx_dblT.t(), out=dconv2, accumulate=True)                            # :277

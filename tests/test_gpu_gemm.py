@@ -9,6 +9,15 @@ from util import assert_close
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["all", "auto"])
+def _gemm_mode(request, monkeypatch):
+    """every autograd-level test runs with all products on the native kernel and with the default routing (token-axis
+    contractions native, the rest library); the raw gemm() tests do not depend on it."""
+    from segmamba_b200 import gemm as G
+    monkeypatch.setattr(G, "MODE", request.param)
+    yield
+
+
 def _mk(rows, cols, major, dtype, seed):
     g = torch.Generator(device="cuda").manual_seed(seed)
     if major == "k":

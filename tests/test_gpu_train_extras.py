@@ -64,7 +64,11 @@ def test_master_weights_step_matches_autocast_step():
     sd = mw.state_dict()
     for k, v in ref_model.state_dict().items():
         assert sd[k].dtype == v.dtype
-        assert_close(sd[k], v, 2e-2, k)
+        # parameters that start at zero (LayerNorm / conv biases) hold nothing but three small, cancellation-dominated gradient
+        # sums after three steps: the two runs' fp32 atomics and bf16 roundings differ there by a sizeable fraction of a tiny
+        # value (0.18 of 1e-3 seen on hardware), so an absolute floor goes with the relative bound
+        err = float((sd[k].float() - v.float()).abs().max())
+        assert err <= 2e-2 * float(v.float().abs().max()) + 5e-4, f"{k}: abs err {err:.3e}"
 
 
 def test_fp16_gradscaler_step_matches_bf16_step():
