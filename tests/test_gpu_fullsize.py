@@ -27,6 +27,17 @@ def _ref_tools():
 
 
 @pytest.fixture
+def ref_kernels():
+    """bind the oracle's two kernel entry points to the reference CUDA extensions for one test, then restore the CPU checker
+    (other test files use the oracle on CPU tensors)"""
+    from oracle import oracle as orc
+    saved = (orc.selective_scan, orc.causal_conv1d)
+    _ref_tools().bind_reference_kernels(orc)
+    yield orc
+    orc.selective_scan, orc.causal_conv1d = saved
+
+
+@pytest.fixture
 def exact_fp32():
     old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
@@ -35,10 +46,9 @@ def exact_fp32():
 
 
 @needs_ref
-def test_config2_default_model_128_fp32_vs_reference_cuda(exact_fp32):
-    from oracle import oracle as orc
+def test_config2_default_model_128_fp32_vs_reference_cuda(exact_fp32, ref_kernels):
     from segmamba_b200.segmamba import SegMamba
-    _ref_tools().bind_reference_kernels(orc)
+    orc = ref_kernels
     torch.manual_seed(0)
     m = SegMamba(in_chans=4, out_chans=4, depths=[2, 2, 2, 2], feat_size=[48, 96, 192, 384]).cuda().eval()
     sd = {k: v.detach().clone().contiguous() for k, v in m.state_dict().items()}
@@ -102,11 +112,10 @@ def _step_loss_and_gradnorm(forward, params, x, y):
 
 
 @needs_ref
-def test_full_size_bf16_training_step_vs_reference_kernels():
-    from oracle import oracle as orc
+def test_full_size_bf16_training_step_vs_reference_kernels(ref_kernels):
     from segmamba_b200 import selective_scan_cuda as ssc
     from segmamba_b200.segmamba import SegMamba
-    _ref_tools().bind_reference_kernels(orc)
+    orc = ref_kernels
     torch.manual_seed(0)
     m = SegMamba(in_chans=4, out_chans=4, depths=[2, 2, 2, 2], feat_size=[48, 96, 192, 384]).cuda().train()
     x = torch.rand(2, 4, 128, 128, 128, device="cuda")
