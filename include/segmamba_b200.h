@@ -304,6 +304,15 @@ typedef struct smb_gemm_args {
 
 SMB_API int smb_gemm(const smb_gemm_args *args, void *cuda_stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Strided 2-D copy, 16-byte vectors: `rows` rows of `row_bytes` bytes from src (row pitch src_pitch_bytes) to dst (row
+ * pitch dst_pitch_bytes).  Pointers, pitches and row_bytes must be multiples of 16.  Replaces the generic strided ATen copies
+ * behind torch.cat((up, skip), dim=1) of UnetrUpBlock (monai/networks/blocks/unetr_block.py:81-86) and its backward on
+ * channels-last activations: a channel concatenation is two such copies into the (tokens, C1 + C2) result.
+ * ---------------------------------------------------------------------------------------------- */
+SMB_API int smb_copy2d(const void *src, int64_t src_pitch_bytes, void *dst, int64_t dst_pitch_bytes, int64_t rows, int64_t row_bytes,
+                       void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

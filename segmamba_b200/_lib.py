@@ -121,6 +121,7 @@ EXPORTS = {
     "smb_layernorm_fwd": (ctypes.c_int, [ctypes.POINTER(LayerNormArgs), _vp]),
     "smb_layernorm_bwd": (ctypes.c_int, [ctypes.POINTER(LayerNormBwdArgs), _vp]),
     "smb_gemm": (ctypes.c_int, [ctypes.POINTER(GemmArgs), _vp]),
+    "smb_copy2d": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
 }
 
 _lib = None

@@ -416,4 +416,18 @@ SMB_API int smb_gemm(const smb_gemm_args *a, void *cuda_stream) {
     return SMB_OK;
 }
 
+SMB_API int smb_copy2d(const void *src, int64_t src_pitch_bytes, void *dst, int64_t dst_pitch_bytes, int64_t rows, int64_t row_bytes,
+                       void *cuda_stream) {
+    if (!src || !dst) return fail(SMB_EINVAL, "smb_copy2d: src and dst are required");
+    if (rows < 0 || row_bytes <= 0) return fail(SMB_EINVAL, "smb_copy2d: bad extent");
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)src_pitch_bytes | (uintptr_t)dst_pitch_bytes |
+          (uintptr_t)row_bytes) & 15) != 0)
+        return fail(SMB_EINVAL, "smb_copy2d: pointers, pitches and row_bytes must be multiples of 16 bytes");
+    if (src_pitch_bytes < row_bytes || dst_pitch_bytes < row_bytes) return fail(SMB_EINVAL, "smb_copy2d: pitch smaller than the row");
+    if (rows == 0) return SMB_OK;
+    cudaError_t e = smb::copy2d_launch(src, src_pitch_bytes, dst, dst_pitch_bytes, rows, row_bytes, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "smb_copy2d");
+    return SMB_OK;
+}
+
 }  // extern "C"

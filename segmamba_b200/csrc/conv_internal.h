@@ -21,6 +21,9 @@ cudaError_t conv1d_v2_dispatch(const ConvP &p, int dtype, bool bwd, cudaStream_t
 // 4-byte-access variant for 16-bit activations (conv1d_v2.cu); cudaErrorNotSupported = shape / alignment not eligible
 cudaError_t seq_permute_v2_dispatch(const void *src, void *dst, int64_t src_rs, int64_t dst_rs, int rows, int L, int ns, int inverse,
                                     int accumulate, int dtype, cudaStream_t st);
+// layout.cu: rows x row_bytes strided copy, 16-byte vectors
+cudaError_t copy2d_launch(const void *src, int64_t src_pitch_bytes, void *dst, int64_t dst_pitch_bytes, int64_t rows, int64_t row_bytes,
+                          cudaStream_t st);
 cudaError_t seq_permute_dispatch(const void *src, void *dst, int64_t src_rs, int64_t dst_rs, int rows, int L, int ns,
                                  int inverse, int accumulate, int dtype, cudaStream_t st);
 

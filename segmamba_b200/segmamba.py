@@ -22,6 +22,7 @@ import torch.nn.functional as F
 
 from . import gemm as _gemm
 from . import layer_norm
+from . import layout as _layout
 from .instance_norm import fused_instance_norm
 from .mamba_simple import Mamba
 
@@ -103,7 +104,10 @@ class UnetrUpBlock(nn.Module):
 
     def forward(self, inp, skip):
         out = self.transp_conv(inp)
-        out = torch.cat((out, skip), dim=1)
+        if _layout.supported(out, skip):                    # channels-last, 16-bit or fp32 rows of 16-byte multiples: native copies
+            out = _layout.cat_channels(out, skip)
+        else:
+            out = torch.cat((out, skip), dim=1)
         return self.conv_block(out)
 
 
