@@ -598,6 +598,8 @@ def main_sliding_window(args):
     if world > 1:
         import datetime
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]               # both levels print a version banner on stdout; keep it to the JSON line
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         os.environ.setdefault("NCCL_MNNVL_ENABLE", "0")
         _start_stall_watchdog(rank, 600.0)
