@@ -227,12 +227,13 @@ def scan_bwd_bytes(meta):
     return s * batch * L * (streams * dim + 2 * N) + 2 * 4 * batch * N * L + 4 * batch * (nck + 1) * N * dim
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per call (all passes of the op) from the committed `ncu --set full` captures,
-# keyed by (op, batch, dim, L, N, element bytes).  Constants from a profiler run, not measured by this script.
-NCU_DRAM_SOURCE = "profiles/r1_ncu_kernels_final_summary.txt (ncu --set full, r9 fwd / r6 bwd captures)"
+# dram__bytes_read.sum + dram__bytes_write.sum per call (all passes of the op) from the committed `ncu --set full` capture of this
+# round, keyed by (op, batch, dim, L, N, element bytes).  Constants from a profiler run of the same kernels (tools/profile_step.py
+# --what scan), not measured by this script; a launch whose key is not listed reports traffic null.
+NCU_DRAM_SOURCE = "profiles/r2l_ncu_scan_summary.txt (ncu --set full, slot r2l: agg2 + main2 forward; ragg2 + main2<dense> backward)"
 NCU_DRAM_BYTES = {
-    ("scan_fwd", 2, 96, 262144, 16, 2): int((218.2 + 16.49 + 348.9 + 95.61) * 1e6),
-    ("scan_bwd", 2, 96, 262144, 16, 2): int((322.0 + 21.53 + 713.4 + 484.6) * 1e6),
+    ("scan_fwd", 2, 96, 262144, 16, 2): int((218.3 + 16.28 + 352.9 + 463.1) * 1e6),     # incl. the 402 MB dense checkpoint write
+    ("scan_bwd", 2, 96, 262144, 16, 2): int((320.0 + 362.8 + 1316.0 + 357.9) * 1e6),    # incl. dense checkpoints: mdense write, hdense + mdense reads
 }
 
 _T0 = time.time()
