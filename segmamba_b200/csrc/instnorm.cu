@@ -22,11 +22,27 @@ constexpr int kNormThreads = 256;
 #ifndef SMB_IN_FWD_MINB
 #define SMB_IN_FWD_MINB 3
 #endif
+// backward kernels, by second-operand mode (slot r2o, tools/norm_bench.py: at (2, 48, 128^3) bf16 the single-operand backward goes
+// 0.535 -> 0.476 ms with 5 resident CTAs and one row in flight, the raw-residual one 0.625 -> 0.567 ms with 4; the two-norm one
+// spills beyond 2 and stays there)
 #ifndef SMB_IN_BWD_MINB0
-#define SMB_IN_BWD_MINB0 3
+#define SMB_IN_BWD_MINB0 5
+#endif
+#ifndef SMB_IN_BWD_MINB1
+#define SMB_IN_BWD_MINB1 4
 #endif
 #ifndef SMB_IN_BWD_MINB2
 #define SMB_IN_BWD_MINB2 2
+#endif
+// rows in flight per thread in the apply / backward-sum passes (memory-level parallelism against registers)
+#ifndef SMB_IN_U_FWD
+#define SMB_IN_U_FWD 2
+#endif
+#ifndef SMB_IN_U_BWD0
+#define SMB_IN_U_BWD0 1
+#endif
+#ifndef SMB_IN_U_BWD2
+#define SMB_IN_U_BWD2 1
 #endif
 
 __device__ __forceinline__ float act_fwd(float v, int act, float slope) {
@@ -232,7 +248,7 @@ __global__ void __launch_bounds__(kNormThreads, SMB_IN_FWD_MINB) in_apply_fwd_ke
             rs2[v] = p.stats2[((int64_t)b * C + c) * 2 + 1];
         }
     }
-    constexpr int U = 2;
+    constexpr int U = SMB_IN_U_FWD;
     for (int64_t row0 = m.row_lo + m.r; row0 < m.row_hi; row0 += (int64_t)U * m.RB) {
         float a[U][V], b2[U][V];
 #pragma unroll
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(kNormThreads, SMB_IN_FWD_MINB) in_apply_fwd_ke
 // partial layout: [batch][cta][3][C]
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : SMB_IN_BWD_MINB2)) in_stats_bwd_kernel(const NormP p) {
+__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : (MODE2 == 1 ? SMB_IN_BWD_MINB1 : SMB_IN_BWD_MINB2))) in_stats_bwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     extern __shared__ float sm[];
     const int C = p.channels, CV = C / V;
@@ -290,7 +306,7 @@ __global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 :
         sg[v] = sgx[v] = sgx2[v] = 0.f;
     }
     if (m.active) {
-        constexpr int U = MODE2 == 0 ? 2 : 1;
+        constexpr int U = MODE2 == 0 ? SMB_IN_U_BWD0 : SMB_IN_U_BWD2;
         for (int64_t row0 = m.row_lo + m.r; row0 < m.row_hi; row0 += (int64_t)U * m.RB) {
             float a[U][V], a2[U][V], g[U][V];
 #pragma unroll
@@ -365,7 +381,7 @@ __global__ void __launch_bounds__(1024) in_finalize_bwd_kernel(const float *__re
 
 // backward apply: dx = rstd (g - mean g - xhat mean(g xhat)) ;  dx2 likewise (mode 2) or dx2 = g (mode 1)
 template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : SMB_IN_BWD_MINB2)) in_apply_bwd_kernel(const NormP p) {
+__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : (MODE2 == 1 ? SMB_IN_BWD_MINB1 : SMB_IN_BWD_MINB2))) in_apply_bwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     const int C = p.channels, CV = C / V;
     const RowMap m = row_map(p, CV);
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 :
         mgx[v] = p.sums[((int64_t)b * C + c) * 3 + 1];
         mgx2[v] = p.sums[((int64_t)b * C + c) * 3 + 2];
     }
-    constexpr int U = MODE2 == 0 ? 2 : 1;
+    constexpr int U = MODE2 == 0 ? SMB_IN_U_BWD0 : SMB_IN_U_BWD2;
     for (int64_t row0 = m.row_lo + m.r; row0 < m.row_hi; row0 += (int64_t)U * m.RB) {
         float a[U][V], a2[U][V], g[U][V];
 #pragma unroll
