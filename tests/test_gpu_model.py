@@ -132,7 +132,8 @@ def test_graphed_train_step_matches_eager():
     y = torch.randint(0, 4, (2, 32, 32, 32), device="cuda")
     o1 = torch.optim.SGD(m1.parameters(), lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5)
     o2 = torch.optim.SGD(m2.parameters(), lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5)
-    step = GraphedTrainStep(m2, o2, torch.nn.functional.cross_entropy, x, y, warmup_iters=3)   # 3 warm-up + 1 captured step
+    step = GraphedTrainStep(m2, o2, torch.nn.functional.cross_entropy, x, y, warmup_iters=3,
+                            restore_after_warmup=False)                             # 3 warm-up steps stay applied
     for _ in range(2):
         loss_g = step(x, y)
     for _ in range(5):                                   # 3 warm-up + 2 replays = the same 5 steps, eagerly
@@ -149,3 +150,32 @@ def test_graphed_train_step_matches_eager():
     num = sum(float((p1.double() - p2.double()).pow(2).sum()) for p1, p2 in zip(m1.parameters(), m2.parameters()))
     den = sum(float(p1.double().pow(2).sum()) for p1 in m1.parameters())
     assert (num / den) ** 0.5 < 1e-2, (num / den) ** 0.5
+
+
+def test_graphed_train_step_with_scheduler_and_restored_state():
+    """a scheduler must keep acting on a graphed step (the optimizer step then runs outside the graph), and the warm-up must not
+    leave a trace: three graphed iterations with the reference's poly schedule == three eager TrainStep iterations from the same
+    initial state (losses; the parameters up to atomics / bf16 noise)."""
+    import copy
+    from segmamba_b200.graph_step import GraphedTrainStep
+    from segmamba_b200.segmamba import SegMamba
+    from segmamba_b200.train_step import PolyLRScheduler, TrainStep
+    c = gi.MODEL_CASE
+    torch.manual_seed(1)
+    m1 = SegMamba(in_chans=4, out_chans=4, depths=c["depths"], feat_size=c["feat_size"], hidden_size=c["hidden_size"]).cuda().train()
+    m2 = copy.deepcopy(m1)
+    mk = lambda m: torch.optim.SGD(m.parameters(), lr=1e-2, momentum=0.99, nesterov=True, weight_decay=3e-5)
+    o1, o2 = mk(m1), mk(m2)
+    s1, s2 = PolyLRScheduler(o1, 1e-2, 4), PolyLRScheduler(o2, 1e-2, 4)
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.rand(2, 4, 32, 32, 32, generator=g).cuda() for _ in range(3)]
+    ys = [torch.randint(0, 4, (2, 32, 32, 32), generator=g).cuda() for _ in range(3)]
+    eager = TrainStep(m1, o1, torch.nn.CrossEntropyLoss(), scheduler=s1)
+    graphed = GraphedTrainStep(m2, o2, torch.nn.functional.cross_entropy, xs[0], ys[0], warmup_iters=3, scheduler=s2)
+    for x, y in zip(xs, ys):
+        le, lg = float(eager(x, y)), float(graphed(x, y))
+        assert abs(le - lg) <= 2e-2 * abs(le), (le, lg)
+    assert o1.param_groups[0]["lr"] == o2.param_groups[0]["lr"] and o2.param_groups[0]["lr"] < 1e-2
+    num = sum(float((p1.double() - p2.double()).pow(2).sum()) for p1, p2 in zip(m1.parameters(), m2.parameters()))
+    den = sum(float(p1.double().pow(2).sum()) for p1 in m1.parameters())
+    assert (num / den) ** 0.5 < 2e-3
