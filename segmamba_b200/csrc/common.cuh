@@ -90,6 +90,16 @@ __device__ __forceinline__ float softplus20(float x) {
     return fmaf(2.f * s, p, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// 1 - exp(-x) for x >= 0 (= sigmoid(raw) when x = softplus(raw)): Taylor polynomial below 1/8 (remainder x^6/720 < 6e-9
+// relative), 1 - ex2 above (cancellation error < 6e-8 / 0.117); ~9 instructions against expm1f's ~25
+__device__ __forceinline__ float one_minus_exp_neg(float x) {
+    float p = fmaf(x, -1.f / 120.f, 1.f / 24.f);
+    p = fmaf(p, -x, 1.f / 6.f);
+    p = fmaf(p, -x, 0.5f);
+    p = fmaf(p, -x, 1.f);
+    const float big = 1.f - __expf(-x);
+    return x < 0.125f ? p * x : big;
+}
 
 // ---------------------------------------------------------------------------------------------
 // element conversion

@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kW * 32, 2) scan_bwd_main2_kernel(const ScanP 
     for (int i = 0; i < kRun; ++i) {
         duv[i] = fmaf(dt[i], sLB[i], Dv * gg[i]);
         float ddt = fmaf(uu[i], sLB[i], kLn2 * sAq[i]);
-        if (p.softplus) ddt *= -expm1f(-dt[i]);          // sigmoid(raw) == 1 - exp(-softplus(raw))
+        if (p.softplus) ddt *= one_minus_exp_neg(dt[i]); // sigmoid(raw) == 1 - exp(-softplus(raw))
         if (jl + i >= L) ddt = 0.f;
         ddv[i] = ddt;
         dDacc = fmaf(gg[i], uu[i], dDacc);
