@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const int as = tc & 1;
             mbar_wait_prof(&tfull[as], (tc >> 1) & 1, (p.prof && lane == 0 && half == 0) ? p.prof + 3 + q : nullptr);
             tc_fence_after();
+            const long long t_tile0 = p.prof ? clock64() : 0;
             const unsigned taddr = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(as * BN);
             const int n0 = nb * BN;
             const int m0 = mb * kBM + q * 32;             // first row of this warp
@@ -322,7 +323,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     for (int h = 0; h < kGC / 32; ++h) {
                         const int c0 = g0 + 32 * h;
                         if (c0 < g_end) {
+                            const long long tq0 = p.prof ? clock64() : 0;
                             tc_wait_ld();
+                            const long long tq1 = p.prof ? clock64() : 0;
+                            if (p.prof && warp == 2 && lane == 0) atomicAdd(p.prof + 8, (unsigned long long)(tq1 - tq0));
                             float v[32];
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cur[i]);
@@ -356,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         }
                     }
                     __syncwarp();
+                    const long long tq2 = p.prof ? clock64() : 0;
                     // ---- write the group out: lane -> (row = 4 it + lane / 8, 16-byte piece = lane % 8) ----
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
@@ -403,8 +408,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         }
                     }
                     __syncwarp();
+                    if (p.prof && warp == 2 && lane == 0) atomicAdd(p.prof + 10, (unsigned long long)(clock64() - tq2));
                 }
             }
+            if (p.prof && warp == 2 && lane == 0) atomicAdd(p.prof + 11, (unsigned long long)(clock64() - t_tile0));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);      // accumulator buffer drained: the MMA warp may reuse it
