@@ -16,14 +16,6 @@
 // across the 2 M-voxel reduction).
 #include "norm_internal.h"
 
-#ifndef SMB_EMU
-#include <cooperative_groups.h>
-
-#include <map>
-#include <mutex>
-#include <utility>
-#endif
-
 namespace smb {
 
 constexpr int kNormThreads = 256;
@@ -108,7 +100,7 @@ __device__ __forceinline__ RowMap row_map(const NormP &p, int CV) {
 // partial layout: [which][batch][cta][3][C]
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool kTwo>
-__device__ __forceinline__ void stats_fwd_body(const NormP &p) {
+__global__ void __launch_bounds__(kNormThreads) in_stats_fwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     extern __shared__ float sm[];                        // [RB][C] x (2 or 4)
     const int C = p.channels, CV = C / V;
@@ -191,9 +183,6 @@ __device__ __forceinline__ void stats_fwd_body(const NormP &p) {
     }
 }
 
-template <typename T, bool kTwo>
-__global__ void __launch_bounds__(kNormThreads) in_stats_fwd_kernel(const NormP p) { stats_fwd_body<T, kTwo>(p); }
-
 // merge the per-CTA (n, mean, M2) with Chan's parallel formula -> (mean, rstd).
 // Block = 32 channels x 32 partial-groups (coalesced 128-byte reads along the channel axis); grid = (C/32, batch, which).
 __global__ void __launch_bounds__(1024) in_finalize_fwd_kernel(const float *__restrict__ partial, float *__restrict__ stats,
@@ -237,7 +226,7 @@ __global__ void __launch_bounds__(1024) in_finalize_fwd_kernel(const float *__re
 // forward apply: y = act( (x - mean) rstd  [+ (x2 - mean2) rstd2 | + x2] )
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE2>
-__device__ __forceinline__ void apply_fwd_body(const NormP &p) {
+__global__ void __launch_bounds__(kNormThreads, SMB_IN_FWD_MINB) in_apply_fwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     const int C = p.channels, CV = C / V;
     const RowMap m = row_map(p, CV);
@@ -288,15 +277,12 @@ __device__ __forceinline__ void apply_fwd_body(const NormP &p) {
     }
 }
 
-template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, SMB_IN_FWD_MINB) in_apply_fwd_kernel(const NormP p) { apply_fwd_body<T, MODE2>(p); }
-
 // ---------------------------------------------------------------------------------------------
 // backward sums: per-CTA  sum g, sum g*xhat1 (, sum g*xhat2)  with g = dy * act'(pre-activation)
 // partial layout: [batch][cta][3][C]
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE2>
-__device__ __forceinline__ void stats_bwd_body(const NormP &p) {
+__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : (MODE2 == 1 ? SMB_IN_BWD_MINB1 : SMB_IN_BWD_MINB2))) in_stats_bwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     extern __shared__ float sm[];
     const int C = p.channels, CV = C / V;
@@ -370,11 +356,6 @@ __device__ __forceinline__ void stats_bwd_body(const NormP &p) {
     }
 }
 
-template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : (MODE2 == 1 ? SMB_IN_BWD_MINB1 : SMB_IN_BWD_MINB2))) in_stats_bwd_kernel(const NormP p) {
-    stats_bwd_body<T, MODE2>(p);
-}
-
 // sums[b][c] = (mean g, mean g*xhat1, mean g*xhat2); same 32 x 8 mapping as the forward finalize
 __global__ void __launch_bounds__(1024) in_finalize_bwd_kernel(const float *__restrict__ partial, float *__restrict__ sums, int batch,
                                                               int C, int n_cta, float inv_n) {
@@ -400,7 +381,7 @@ __global__ void __launch_bounds__(1024) in_finalize_bwd_kernel(const float *__re
 
 // backward apply: dx = rstd (g - mean g - xhat mean(g xhat)) ;  dx2 likewise (mode 2) or dx2 = g (mode 1)
 template <typename T, int MODE2>
-__device__ __forceinline__ void apply_bwd_body(const NormP &p) {
+__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : (MODE2 == 1 ? SMB_IN_BWD_MINB1 : SMB_IN_BWD_MINB2))) in_apply_bwd_kernel(const NormP p) {
     constexpr int V = VecOf<T>::V;
     const int C = p.channels, CV = C / V;
     const RowMap m = row_map(p, CV);
@@ -461,123 +442,6 @@ __device__ __forceinline__ void apply_bwd_body(const NormP &p) {
     }
 }
 
-template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, (MODE2 == 0 ? SMB_IN_BWD_MINB0 : (MODE2 == 1 ? SMB_IN_BWD_MINB1 : SMB_IN_BWD_MINB2))) in_apply_bwd_kernel(const NormP p) {
-    apply_bwd_body<T, MODE2>(p);
-}
-
-#ifndef SMB_EMU
-// ---------------------------------------------------------------------------------------------
-// Small tensors (everything fits the 126 MB L2: the 64^3 ... 8^3 stages, 43 of the model's calls per pass): the three passes
-// in ONE cooperative launch -- statistics, grid barrier, merge (each CTA merges the partials of its share of the channels),
-// grid barrier, apply (second read served by L2).  Three launches of 5-25 us each were 4.1 ms of the step for 10 MB-scale
-// tensors (profiles/r2z_op_breakdown.txt).  cudaLaunchCooperativeKernel guarantees co-residency or fails, it never hangs.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void finalize_fwd_in_grid(const NormP &p, bool two) {
-    const int C = p.channels, b = blockIdx.y, n_cta = gridDim.x;
-    for (int which = 0; which < (two ? 2 : 1); ++which) {
-        for (int c = blockIdx.x * kNormThreads + threadIdx.x; c < C; c += gridDim.x * kNormThreads) {
-            const float *pp = p.partial + (int64_t)which * p.batch * n_cta * 3 * C + ((int64_t)b * n_cta * 3) * C + c;
-            double dn = 0.0, dmean = 0.0, dM2 = 0.0;
-            for (int k = 0; k < n_cta; ++k) {
-                const double nk = pp[(int64_t)k * 3 * C], mk = pp[(int64_t)k * 3 * C + C], qk = pp[(int64_t)k * 3 * C + 2 * C];
-                if (nk <= 0.0) continue;
-                const double nt = dn + nk, dlt = mk - dmean;
-                dmean += dlt * nk / nt;
-                dM2 += qk + dlt * dlt * dn * nk / nt;
-                dn = nt;
-            }
-            const double var = dn > 0.0 ? dM2 / dn : 0.0;
-            float *o = (which ? p.stats2 : p.stats) + ((int64_t)b * C + c) * 2;
-            o[0] = (float)dmean;
-            o[1] = (float)(1.0 / sqrt(var + (double)p.eps));
-        }
-    }
-}
-__device__ __forceinline__ void finalize_bwd_in_grid(const NormP &p) {
-    const int C = p.channels, b = blockIdx.y, n_cta = gridDim.x;
-    const double inv_n = 1.0 / (double)p.spatial;
-    for (int c = blockIdx.x * kNormThreads + threadIdx.x; c < C; c += gridDim.x * kNormThreads) {
-        const float *pp = p.partial + ((int64_t)b * n_cta * 3) * C + c;
-        double da = 0.0, dq = 0.0, dq2 = 0.0;
-        for (int k = 0; k < n_cta; ++k) { da += pp[(int64_t)k * 3 * C]; dq += pp[(int64_t)k * 3 * C + C]; dq2 += pp[(int64_t)k * 3 * C + 2 * C]; }
-        float *o = p.sums + ((int64_t)b * C + c) * 3;
-        o[0] = (float)(da * inv_n); o[1] = (float)(dq * inv_n); o[2] = (float)(dq2 * inv_n);
-    }
-}
-template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, 2) in_fused_fwd_kernel(const NormP p) {
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    stats_fwd_body<T, MODE2 == 2>(p);
-    __threadfence();
-    grid.sync();
-    finalize_fwd_in_grid(p, MODE2 == 2);
-    __threadfence();
-    grid.sync();
-    apply_fwd_body<T, MODE2>(p);
-}
-template <typename T, int MODE2>
-__global__ void __launch_bounds__(kNormThreads, 2) in_fused_bwd_kernel(const NormP p) {
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    stats_bwd_body<T, MODE2>(p);
-    __threadfence();
-    grid.sync();
-    finalize_bwd_in_grid(p);
-    __threadfence();
-    grid.sync();
-    apply_bwd_body<T, MODE2>(p);
-}
-
-// co-resident CTAs of a kernel instance (queried once per instance)
-template <typename K>
-static int max_coresident(K kernel, size_t smem) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kNormThreads, smem) != cudaSuccess) return 0;
-    return per_sm * sms;
-}
-// SMB_IN_FUSED=0 keeps three launches for every size (A/B); the byte threshold counts every activation operand of the call
-static bool fused_wanted(const NormP &p, int elem_bytes, bool bwd) {
-    static const bool on = [] { const char *e = getenv("SMB_IN_FUSED"); return !(e && e[0] == '0'); }();
-    if (!on) return false;
-    const int operands = (bwd ? 2 : 1) + (p.mode2 ? 1 : 0);
-    return (double)p.batch * p.channels * (double)p.spatial * elem_bytes * operands <= 96e6;
-}
-template <typename K>
-static cudaError_t launch_fused(K kernel, NormP p, size_t smem, int elem_bytes, cudaStream_t st, bool *done) {
-    *done = false;
-    int cap;
-    {   // co-resident capacity per (kernel instance, shared-memory size): queried once, under a lock (the ABI is re-entrant)
-        static std::mutex mu;
-        static std::map<std::pair<const void *, size_t>, int> caps;
-        std::lock_guard<std::mutex> lock(mu);
-        const auto key = std::make_pair(reinterpret_cast<const void *>(kernel), smem);
-        auto it = caps.find(key);
-        if (it == caps.end()) {
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            it = caps.emplace(key, max_coresident(kernel, smem)).first;
-        }
-        cap = it->second;
-    }
-    int n_cta = cap / p.batch;
-    if (n_cta < 1) return cudaSuccess;                        // not co-residable: the caller takes the three-launch path
-    if (n_cta > p.n_cta) n_cta = p.n_cta;                     // the workspace holds partials for p.n_cta CTAs per batch
-    const int V = 16 / elem_bytes, RB = kNormThreads / (p.channels / V);
-    int64_t rows = (p.spatial + n_cta - 1) / n_cta;
-    if (rows < (int64_t)RB * 2) rows = (int64_t)RB * 2;
-    p.rows_per_cta = rows;
-    p.n_cta = (int)((p.spatial + rows - 1) / rows);
-    dim3 grid(p.n_cta, p.batch);
-    void *args[] = {&p};
-    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kernel), grid, dim3(kNormThreads), args, smem, st);
-    if (e != cudaSuccess) return e;
-    count_launch();
-    *done = true;
-    return cudaSuccess;
-}
-#endif  // !SMB_EMU
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -588,16 +452,6 @@ static cudaError_t norm_fwd_t(NormP p, cudaStream_t st) {
     dim3 grid(p.n_cta, p.batch);
     const bool two = p.mode2 == 2;
     const size_t smem = (size_t)RB * p.channels * (two ? 4 : 2) * sizeof(float);
-#ifndef SMB_EMU
-    if (fused_wanted(p, (int)sizeof(T), false)) {
-        bool done = false;
-        cudaError_t e = p.mode2 == 0 ? launch_fused(in_fused_fwd_kernel<T, 0>, p, smem, (int)sizeof(T), st, &done)
-                      : p.mode2 == 1 ? launch_fused(in_fused_fwd_kernel<T, 1>, p, smem, (int)sizeof(T), st, &done)
-                                     : launch_fused(in_fused_fwd_kernel<T, 2>, p, smem, (int)sizeof(T), st, &done);
-        if (e != cudaSuccess) return e;
-        if (done) return cudaGetLastError();
-    }
-#endif
     if (two) in_stats_fwd_kernel<T, true><<<grid, kNormThreads, smem, st>>>(p);
     else in_stats_fwd_kernel<T, false><<<grid, kNormThreads, smem, st>>>(p);
     count_launch();
@@ -617,16 +471,6 @@ static cudaError_t norm_bwd_t(NormP p, cudaStream_t st) {
     const int CV = p.channels / V, RB = kNormThreads / CV;
     dim3 grid(p.n_cta, p.batch);
     const size_t smem = (size_t)RB * p.channels * 3 * sizeof(float);
-#ifndef SMB_EMU
-    if (fused_wanted(p, (int)sizeof(T), true)) {
-        bool done = false;
-        cudaError_t e = p.mode2 == 0 ? launch_fused(in_fused_bwd_kernel<T, 0>, p, smem, (int)sizeof(T), st, &done)
-                      : p.mode2 == 1 ? launch_fused(in_fused_bwd_kernel<T, 1>, p, smem, (int)sizeof(T), st, &done)
-                                     : launch_fused(in_fused_bwd_kernel<T, 2>, p, smem, (int)sizeof(T), st, &done);
-        if (e != cudaSuccess) return e;
-        if (done) return cudaGetLastError();
-    }
-#endif
     if (p.mode2 == 0) in_stats_bwd_kernel<T, 0><<<grid, kNormThreads, smem, st>>>(p);
     else if (p.mode2 == 1) in_stats_bwd_kernel<T, 1><<<grid, kNormThreads, smem, st>>>(p);
     else in_stats_bwd_kernel<T, 2><<<grid, kNormThreads, smem, st>>>(p);
