@@ -43,6 +43,48 @@ def _pointwise(conv: nn.Conv3d, x: torch.Tensor, gelu: bool = False) -> torch.Te
     return F.gelu(y) if gelu else y
 
 
+class _ZeroGradBias(torch.autograd.Function):
+    """identity on ``y`` that keeps ``bias`` in the graph with an exact zero gradient (see ``_conv_before_norm``)."""
+
+    @staticmethod
+    def forward(ctx, y, bias):
+        ctx.bias_meta = (bias.shape, bias.dtype, bias.device)
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, dtype, device = ctx.bias_meta
+        return g, torch.zeros(shape, dtype=dtype, device=device)
+
+
+def _conv_before_norm(conv: nn.Conv3d, x: torch.Tensor) -> torch.Tensor:
+    """``conv(x)`` for a convolution whose output goes straight into an InstanceNorm (GSC, segmamba.py:111-128): its bias is a
+    per-channel constant that the normalisation subtracts again, and the bias gradient -- the per-channel sum of a gradient that
+    has passed through the norm -- is analytically zero.  So the bias is neither added (one full-tensor ATen kernel per
+    convolution) nor reduced in the backward (one reduction per convolution); the parameter stays in the graph with an exact
+    zero gradient, so weight decay acts on it exactly as in the reference and the state_dict surface is unchanged."""
+    if conv.bias is None:
+        return _pointwise(conv, x) if conv.kernel_size == (1, 1, 1) else conv(x)
+    if conv.kernel_size == (1, 1, 1) and _gemm.MODE == "all":
+        y = _pointwise(_BiasFree(conv), x)
+    else:
+        y = F.conv3d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return _ZeroGradBias.apply(y, conv.bias)
+
+
+class _BiasFree:
+    """view of a Conv3d without its bias, for ``_pointwise``"""
+
+    def __init__(self, conv):
+        self.weight, self.bias = conv.weight, None
+        self.kernel_size, self.stride, self.in_channels, self.out_channels = conv.kernel_size, conv.stride, conv.in_channels, conv.out_channels
+        self._conv = conv
+
+    def __call__(self, x):
+        c = self._conv
+        return F.conv3d(x, c.weight, None, c.stride, c.padding, c.dilation, c.groups)
+
+
 class _Conv(nn.Sequential):
     """stand-in for monai Convolution(conv_only-like: act=None, norm=None): a Sequential with one child `conv`."""
 
@@ -186,10 +228,10 @@ class GSC(nn.Module):
 
     def forward(self, x):
         x_residual = x
-        x1 = fused_instance_norm(self.proj(x), "relu")
-        x1 = fused_instance_norm(self.proj2(x1), "relu")
-        x2 = fused_instance_norm(_pointwise(self.proj3, x), "relu")
-        x = fused_instance_norm(_pointwise(self.proj4, x1 + x2), "relu")
+        x1 = fused_instance_norm(_conv_before_norm(self.proj, x), "relu")
+        x1 = fused_instance_norm(_conv_before_norm(self.proj2, x1), "relu")
+        x2 = fused_instance_norm(_conv_before_norm(self.proj3, x), "relu")
+        x = fused_instance_norm(_conv_before_norm(self.proj4, x1 + x2), "relu")
         return x + x_residual
 
 
