@@ -607,3 +607,20 @@ def test_emu_seq_permute_v2(monkeypatch, dtype, L, ns):
         assert torch.equal(f, ref), key
         assert torch.equal(b, x), key
         assert torch.equal(acc, res[("0", 0)][2]), key
+
+
+@pytest.mark.parametrize("opc", ["1", "3"], ids=["opc1", "opc3"])
+@pytest.mark.parametrize("order", [0, 3], ids=["ascending", "random3"])
+def test_emu_scan_dense_checkpoints_and_octet_walk(monkeypatch, opc, order):
+    """scan-free main backward pass on the dense checkpoints (state / local adjoint at every 8th position), one CTA walking 1 or
+    3 channel octets, under two thread orders: all gradients against the oracle (ragged length, partial octet, two B/C groups,
+    both walk directions)."""
+    monkeypatch.setenv("SMB_R3_OPC", opc)
+    emu.emu_lib().smb_emu_set_reverse(order)
+    for shape, direction in (((2, 44, 1003, 16, 1), 0), ((1, 48, 520, 8, 2), 1)):
+        batch, dim, L, N, G = shape
+        d = rand_scan_inputs(700 + L, batch, dim, L, N, G, torch.bfloat16, device="cpu")
+        res = tg._run_fwd_bwd(d, direction=direction, use_hstates=True)
+        ref = tg._oracle_fwd_bwd(d, flip=bool(direction))
+        tg._compare(res, ref, torch.bfloat16, True)
+    emu.emu_lib().smb_emu_set_reverse(0)
